@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- mask-matches/sec of the DMM-Net matching hot path (cost-build + relaxed-matching solve).
+
+Workload (BASELINE.json configs[1]): N=50 proposals, K=10 templates, 256x448 fp32 soft masks, D=512 features,
+20 outer x 5 inner solver iterations, synthetic seeded inputs (dmm_net_b200/synth.py).  One "step" = one pass of the
+hot path (cosine K2 -> mask-IoU K1 (+finalize/mix) -> solver+head K3) over a batch of `--batch` independent problems
+that is ALREADY RESIDENT in HBM.  The batch (B x 27.5 MB) is far larger than the 126 MB L2, so every step streams
+from HBM (no L2 flush needed; stated in config.l2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+N>1 is launched by torchrun (one rank per GPU); ranks shard independent problems (weak scaling, no data-path
+collective); time = max over ranks of the CUDA-event time of exactly K steps.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P, O, H, W, D = 50, 10, 256, 448, 512
+MAX_ITER, PROJ_ITER, LR, SCORE_W = 20, 5, 0.1, 0.3
+MASK_BYTES_PER_MATCH = (P + O) * H * W * 4                       # K1 algorithmic bytes per match: 27,525,120
+ALGO_BYTES_PER_MATCH = MASK_BYTES_PER_MATCH + (P + O) * D * 4 + O * P * 4  # 27,650,000
+METRIC = "mask-matches/sec (cost-build+Sinkhorn, N=50 K=10 256x448)"
+WORKLOAD = "configs[1]: N=50 K=10 256x448 fp32 masks, D=512, 20x5 relaxed-matching iters, cost-build+solve"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_rate(seconds_budget: float, threads: int):
+    """The reference's CPU path (oracle port: same torch-CPU op sequence incl. the [O*P,HW] expansions) on this
+    host's cores: cost-build + solve of the headline problem, timed one problem at a time."""
+    from oracle import match_oracle as orc
+    from dmm_net_b200.synth import make_problem
+    torch.set_num_threads(threads)
+    pr = make_problem(P, O, H, W, D, config=2, index=0)
+
+    def one():
+        with torch.no_grad():
+            sim, _ = orc.cost_matrix(pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, SCORE_W, None, expand=True)
+            _, _, X_list, _ = orc.relax_solve(-sim, MAX_ITER, PROJ_ITER, LR)
+            return sum(X_list) / len(X_list)
+
+    one()                                                            # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        one()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds_budget or n >= 200:
+            break
+    return n / el, n, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the python reference tree
+    does not exist on the GPU box), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step_budget = max(0.5, min(4.0, 60.0 / max(1, args.steps + args.warmup)))
+    from oracle import match_oracle as orc
+    from dmm_net_b200.synth import make_problem
+    torch.set_num_threads(threads)
+    pr = make_problem(P, O, H, W, D, config=2, index=0)
+
+    def one():
+        with torch.no_grad():
+            sim, _ = orc.cost_matrix(pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, SCORE_W, None, expand=True)
+            orc.relax_solve(-sim, MAX_ITER, PROJ_ITER, LR)
+
+    one()
+    t0 = time.perf_counter(); one(); t_one = time.perf_counter() - t0
+    per_step = max(1, int(per_step_budget / max(t_one, 1e-3)))
+    for _ in range(args.warmup):
+        for _ in range(per_step):
+            one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            one()
+    el = time.perf_counter() - t0
+    val = args.steps * per_step / el
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "matches/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "matches_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": "matches/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps}x{per_step} problems of the headline shape, oracle/match_oracle.py "
+                                       f"(torch-CPU port of the reference op sequence, {threads} threads)"},
+            "e2e": {"value": val, "unit": "matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=128, help="independent problems per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (rank 0, N=1)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from dmm_net_b200 import ops
+    from dmm_net_b200.synth import make_problems
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    pr = make_problems(B, P, O, H, W, D, seed=2000 + rank, device=dev)          # synthetic, generated on the device
+    launches = 0
+
+    def hot_path(timers=None):
+        """cost-build + solve for the resident batch; returns the mean-iterate assignment R [B,O,MS]."""
+        nonlocal launches
+        cos = ops.cosine_pairwise(pr.tmpl_feat[:, None], pr.prop_feat)                              # K2: 1 launch
+        if timers is not None:
+            timers[0].record()
+        r = ops.mask_iou_pairwise(pr.prop_mask, pr.tmpl_mask, cos=cos, w_cos=1 - SCORE_W, w_iou=SCORE_W)  # K1: 2 launches
+        if timers is not None:
+            timers[1].record()
+        out = ops.relax_solve(r["sim"], pr.prop_score, None, None, MAX_ITER, PROJ_ITER, LR, True, True, True)  # K3: 1 launch
+        launches += 4
+        return out[0]
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            hot_path()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        launches = 0
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            torch.cuda.synchronize()
+            t_beg.record()
+            for k in range(args.steps):
+                R = hot_path(ev[k])
+            t_end.record()
+            torch.cuda.synchronize()
+        ms_total = t_beg.elapsed_time(t_end)
+        k1_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+        dist.barrier()
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: same metric through the reference-facing module with HOST (pinned) buffers -------------------
+    from dmm_net_b200.modules.match_model import MatchModel
+    from dmm_net_b200.synth import default_cfg
+    layer = MatchModel(default_cfg(MAX_ITER, PROJ_ITER, LR, SCORE_W), is_test=1)
+    Be = min(B, 32)
+    host = {k: getattr(pr, k)[:Be].cpu().pin_memory() for k in ("prop_feat", "prop_mask", "tmpl_feat", "tmpl_mask", "prop_score")}
+    h2d = sum(v.numel() * 4 for v in host.values())
+    res_host = torch.empty(Be, O, max(P, O + 1), pin_memory=True)
+    res_ms = torch.empty(Be, O, pin_memory=True)
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out = layer.forward_many(d["prop_feat"], d["prop_mask"], d["tmpl_feat"], d["tmpl_mask"], d["prop_score"])
+        res_host.copy_(out["R"], non_blocking=True)
+        res_ms.copy_(out["match_score"], non_blocking=True)
+
+    with torch.no_grad():
+        e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        e2e_ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e_val = world * Be * args.e2e_steps / (e2e_ms * 1e-3)
+    d2h = (res_host.numel() + res_ms.numel()) * 4
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = MASK_BYTES_PER_MATCH * B / (k1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "matches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "problems_per_step_per_gpu": B, "parallelism": f"dp{world} (problems sharded, no collective)",
+                       "l2": f"inputs {B * MASK_BYTES_PER_MATCH / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
+                       "full_step_gbs_per_gpu": ALGO_BYTES_PER_MATCH * B / (ms_total / args.steps * 1e-3) / 1e9},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_val, "unit": "matches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "problems_per_step": Be, "api": "MatchModel.forward_many on pinned host tensors (+assignment-apply)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "mask_iou_partial_kernel(+finalize)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": MASK_BYTES_PER_MATCH * B, "kernel_ms": k1_ms},
+        }
+        if world == 1 and args.cpu_seconds > 0:
+            threads = os.cpu_count() or 1
+            rate, n, el = cpu_reference_rate(args.cpu_seconds, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "matches/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n} problems of the headline shape in {el:.1f} s, oracle/match_oracle.py "
+                                              f"(torch-CPU port of the reference op sequence incl. [O*P,HW] expansion)"}
+        prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(prof):
+            try:
+                line["roofline"]["traffic"] = json.load(open(prof)).get("traffic_bytes_per_match", 0) * B or None
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,332 @@
+// K1 -- pairwise binary-mask IoU (reference: dmm/utils/match_helper.py:9-28 over the [O*P, HW] expansion of
+// dmm/modules/match_model.py:83-89; second template set = targets of match_helper.py:30-42).
+//
+// HBM-bound integer kernel.  Every mask byte is read exactly once:
+//   - a CTA owns a pixel slab of ONE problem for ALL of its (<=64) masks;
+//   - phase A: each warp streams 512-byte row pieces (one LDG.128 per lane, next chunk's loads already in
+//     flight), thresholds >0.5 and turns 128 pixels into 4 bit-plane words with __ballot_sync;
+//   - phase B: warp w owns word w of the chunk; lanes are proposals, the O template words are smem
+//     broadcasts: popc(a & b) into O x 2 register counters per lane;
+//   - per-slab int32 partials go to a workspace (no atomics, no memset), a second tiny kernel adds the
+//     slabs and forms  inter / (float(|A|+|B|-inter) + 1e-6f)  -- integer-exact, so bit-equal to the reference.
+#include "common.cuh"
+
+namespace dmm {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunkPx = 256;                 // pixels per pipeline step (2 groups of 128)
+constexpr int kWords = kChunkPx / 32;         // 8 bit-plane words per row per chunk == kWarps
+constexpr int kMaxRows = 64;                  // masks per tile (proposals + templates)
+constexpr int kMaxUnits = kMaxRows * 2 / kWarps;  // 512-byte row pieces per warp per chunk (16)
+constexpr int kTileO = 16;                    // templates per tile (register counters)
+constexpr int kRowPad = kMaxRows + 1;
+static_assert(kWords == kWarps, "one bit-plane word per warp in phase B");
+
+struct IouParams {
+  const float* prop;
+  const float* tmpl;
+  const float* tmpl2;
+  long long prop_bs, tmpl_bs, tmpl2_bs;
+  const int* n_prop;
+  const int* n_tmpl;
+  int P, O, Otot, HW;
+  int PT, OT, n_ptiles, n_otiles;  // tile sizes / counts
+  int S, chunks_per_slab, n_chunks;
+  int* ws;                         // [B][S][cnt]
+  int cnt;                         // Otot*P + Otot + P
+};
+
+template <bool VEC>
+__device__ __forceinline__ float4 load_px4(const float* row, int px, int HW) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row == nullptr) return v;
+  if (VEC) {
+    if (px < HW) v = ld_stream_f4(row + px);
+  } else {
+    if (px + 0 < HW) v.x = ld_stream_f1(row + px + 0);
+    if (px + 1 < HW) v.y = ld_stream_f1(row + px + 1);
+    if (px + 2 < HW) v.z = ld_stream_f1(row + px + 2);
+    if (px + 3 < HW) v.w = ld_stream_f1(row + px + 3);
+  }
+  return v;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const IouParams p) {
+  __shared__ const float* row_ptr[kMaxRows];
+  __shared__ uint32_t bits[2][kWords][kRowPad];
+  __shared__ int red[kTileO * kMaxRows + kMaxRows];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int ptile = blockIdx.z % p.n_ptiles, otile = blockIdx.z / p.n_ptiles;
+  const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
+  const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
+  const int p0 = ptile * p.PT, o0 = otile * p.OT;
+  const int pcnt = min(p.PT, p.P - p0), ocnt = min(p.OT, p.Otot - o0);
+  const int rows = pcnt + ocnt, units = rows * 2;
+
+  if (tid < kMaxRows) {
+    const float* ptr = nullptr;
+    if (tid < pcnt) {
+      if (p0 + tid < np) ptr = p.prop + (long long)b * p.prop_bs + (long long)(p0 + tid) * p.HW;
+    } else if (tid < rows) {
+      const int t = o0 + tid - pcnt;
+      if (t < p.O) {
+        if (t < nt) ptr = p.tmpl + (long long)b * p.tmpl_bs + (long long)t * p.HW;
+      } else if (t - p.O < nt) {
+        ptr = p.tmpl2 + (long long)b * p.tmpl2_bs + (long long)(t - p.O) * p.HW;
+      }
+    }
+    row_ptr[tid] = ptr;
+  }
+  for (int i = tid; i < 2 * kWords * kRowPad; i += kThreads) (&bits[0][0][0])[i] = 0u;
+  for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kThreads) red[i] = 0;
+  __syncthreads();
+
+  const int c0 = s * p.chunks_per_slab;
+  const int c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
+
+  int acc[kTileO][2];
+#pragma unroll
+  for (int o = 0; o < kTileO; ++o) acc[o][0] = acc[o][1] = 0;
+  int area0 = 0, area1 = 0;  // popcount of row `lane` and row `lane+32` (covers proposals AND templates)
+
+  float4 v[kMaxUnits];
+  auto issue = [&](int chunk) {
+#pragma unroll
+    for (int k = 0; k < kMaxUnits; ++k) {
+      const int u = warp + kWarps * k;
+      if (u < units) {
+        const int px = chunk * kChunkPx + (u & 1) * 128 + lane * 4;
+        v[k] = load_px4<VEC>(row_ptr[u >> 1], px, p.HW);
+      }
+    }
+  };
+
+  if (c0 < c1) issue(c0);
+  for (int c = c0; c < c1; ++c) {
+    const int buf = (c - c0) & 1;
+    // ---- phase A: threshold + ballot -> bit planes ------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kMaxUnits; ++k) {
+      const int u = warp + kWarps * k;
+      if (u < units) {
+        const uint32_t w0 = __ballot_sync(0xffffffffu, v[k].x > 0.5f);
+        const uint32_t w1 = __ballot_sync(0xffffffffu, v[k].y > 0.5f);
+        const uint32_t w2 = __ballot_sync(0xffffffffu, v[k].z > 0.5f);
+        const uint32_t w3 = __ballot_sync(0xffffffffu, v[k].w > 0.5f);
+        // bit i of word j is pixel 4*i+j of the 128-pixel group: a fixed permutation shared by all rows,
+        // and AND/popcount do not care about bit order.
+        if (lane < 4) {
+          const uint32_t w = lane == 0 ? w0 : (lane == 1 ? w1 : (lane == 2 ? w2 : w3));
+          bits[buf][(u & 1) * 4 + lane][u >> 1] = w;
+        }
+      }
+    }
+    if (c + 1 < c1) issue(c + 1);  // next chunk's loads fly during the barrier and phase B
+    __syncthreads();
+    // ---- phase B: warp w owns word w; lanes are proposals (lane, lane+32) --------------------------------
+    {
+      const uint32_t* wrow = bits[buf][warp];
+      const uint32_t b0 = wrow[lane], b1 = wrow[lane + 32];
+      area0 += __popc(b0);
+      area1 += __popc(b1);
+#pragma unroll
+      for (int o = 0; o < kTileO; ++o) {
+        if (o < ocnt) {
+          const uint32_t a = wrow[pcnt + o];
+          acc[o][0] += __popc(a & b0);
+          acc[o][1] += __popc(a & b1);
+        }
+      }
+    }
+    // the double-buffered bit planes make a second barrier unnecessary: buffer `buf` is rewritten in
+    // iteration c+2, which every warp enters only after the barrier of iteration c+1.
+  }
+
+  // ---- cross-warp reduction of this slab ---------------------------------------------------------------
+#pragma unroll
+  for (int o = 0; o < kTileO; ++o) {
+    if (o < ocnt) {
+      atomicAdd(&red[o * kMaxRows + lane], acc[o][0]);
+      atomicAdd(&red[o * kMaxRows + lane + 32], acc[o][1]);
+    }
+  }
+  atomicAdd(&red[kTileO * kMaxRows + lane], area0);
+  atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
+  __syncthreads();
+
+  int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
+  for (int i = tid; i < ocnt * pcnt; i += kThreads) {
+    const int o = i / pcnt, q = i - o * pcnt;
+    out[(o0 + o) * p.P + p0 + q] = red[o * kMaxRows + q];
+  }
+  int* area_t = out + p.Otot * p.P;
+  int* area_p = area_t + p.Otot;
+  if (ptile == 0)
+    for (int i = tid; i < ocnt; i += kThreads) area_t[o0 + i] = red[kTileO * kMaxRows + pcnt + i];
+  if (otile == 0)
+    for (int i = tid; i < pcnt; i += kThreads) area_p[p0 + i] = red[kTileO * kMaxRows + i];
+}
+
+struct FinParams {
+  const int* ws;
+  int S, cnt, B, P, O, Otot;
+  const int* n_prop;
+  const int* n_tmpl;
+  float* iou;
+  float* iou2;
+  const float* cos;
+  float w_cos, w_iou;
+  float* sim;
+  int* counts;
+};
+
+__global__ void __launch_bounds__(256) mask_iou_finalize_kernel(const FinParams p) {
+  const long long total = (long long)p.B * p.Otot * p.P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % p.P);
+    const int t = (int)((i / p.P) % p.Otot);
+    const int b = (int)(i / ((long long)p.P * p.Otot));
+    const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
+    const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
+    const int o = t < p.O ? t : t - p.O;
+    float r = 0.f;
+    int inter = 0, at = 0, ap = 0;
+    if (q < np && o < nt) {
+      const int* w = p.ws + (long long)b * p.S * p.cnt;
+      for (int s = 0; s < p.S; ++s, w += p.cnt) {
+        inter += w[t * p.P + q];
+        at += w[p.Otot * p.P + t];
+        ap += w[p.Otot * p.P + p.Otot + q];
+      }
+      // match_helper.py:21-27: union.sum()+1e-6 in fp32, IEEE divide.  The counts are exact integers < 2^24.
+      const float uni = __fadd_rn((float)(at + ap - inter), 1e-6f);
+      r = __fdiv_rn((float)inter, uni);
+    }
+    const long long oi = ((long long)b * p.O + o) * p.P + q;
+    if (t < p.O) {
+      if (p.iou) p.iou[oi] = r;
+      if (p.sim) p.sim[oi] = __fadd_rn(__fmul_rn(p.cos[oi], p.w_cos), __fmul_rn(r, p.w_iou));  // match_model.py:90
+      if (p.counts) {
+        int* c = p.counts + (long long)b * (p.O * p.P + p.O + p.P);
+        c[o * p.P + q] = inter;
+        if (q == 0) c[p.O * p.P + o] = at;
+        if (o == 0) c[p.O * p.P + p.O + q] = ap;
+      }
+    } else if (p.iou2) {
+      p.iou2[oi] = r;
+    }
+  }
+}
+
+struct Plan {
+  int PT, OT, n_ptiles, n_otiles, S, n_chunks, chunks_per_slab, cnt, Otot;
+};
+
+Plan make_plan(int B, int P, int O, int HW, int two) {
+  Plan pl;
+  pl.Otot = O * (two ? 2 : 1);
+  pl.OT = pl.Otot < kTileO ? pl.Otot : kTileO;
+  pl.PT = P < kMaxRows - pl.OT ? P : kMaxRows - pl.OT;
+  if (pl.OT < 1) pl.OT = 1;
+  if (pl.PT < 1) pl.PT = 1;
+  pl.n_ptiles = (P + pl.PT - 1) / pl.PT;
+  pl.n_otiles = (pl.Otot + pl.OT - 1) / pl.OT;
+  pl.n_chunks = (HW + kChunkPx - 1) / kChunkPx;
+  if (pl.n_chunks < 1) pl.n_chunks = 1;
+  // enough CTAs for ~4 waves at 2 CTAs/SM, but never slabs shorter than 4 chunks
+  const long long tiles = (long long)B * pl.n_ptiles * pl.n_otiles;
+  long long want = (4LL * 2 * kNumSMs + tiles - 1) / tiles;
+  long long max_s = pl.n_chunks / 4 > 0 ? pl.n_chunks / 4 : 1;
+  long long S = want < 1 ? 1 : (want > max_s ? max_s : want);
+  if (S > 65535) S = 65535;
+  pl.chunks_per_slab = (int)((pl.n_chunks + S - 1) / S);
+  pl.S = (pl.n_chunks + pl.chunks_per_slab - 1) / pl.chunks_per_slab;
+  pl.cnt = pl.Otot * P + pl.Otot + P;
+  return pl;
+}
+
+}  // namespace
+}  // namespace dmm
+
+using namespace dmm;
+
+extern "C" size_t dmm_mask_iou_workspace_bytes(int B, int P, int O, int HW, int two_template_sets) {
+  if (B <= 0 || P <= 0 || O <= 0 || HW <= 0) return 0;
+  const Plan pl = make_plan(B, P, O, HW, two_template_sets);
+  return align_up((size_t)B * pl.S * pl.cnt * sizeof(int), 256);
+}
+
+extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, const float* tmpl,
+                                     long long tmpl_bstride, const float* tmpl2, long long tmpl2_bstride, int B,
+                                     int P, int O, int HW, const int* n_prop, const int* n_tmpl, float* iou,
+                                     float* iou2, const float* cos, float w_cos, float w_iou, float* sim,
+                                     int* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || P < 0 || O < 0 || HW < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (B == 0 || P == 0 || O == 0) return DMM_OK;  // nothing to write
+  if (!prop || !tmpl || !workspace) return DMM_ERR_INVALID_ARGUMENT;
+  if (sim && !cos) return DMM_ERR_INVALID_ARGUMENT;
+  if (iou2 && !tmpl2) return DMM_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
+  const int two = tmpl2 != nullptr;
+  const Plan pl = make_plan(B, P, O, HW > 0 ? HW : 1, two);
+  if (workspace_bytes < (size_t)B * pl.S * pl.cnt * sizeof(int)) return DMM_ERR_WORKSPACE_TOO_SMALL;
+  if (pl.n_ptiles * pl.n_otiles > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  IouParams kp;
+  kp.prop = prop; kp.tmpl = tmpl; kp.tmpl2 = tmpl2;
+  kp.prop_bs = prop_bstride; kp.tmpl_bs = tmpl_bstride; kp.tmpl2_bs = tmpl2_bstride;
+  kp.n_prop = n_prop; kp.n_tmpl = n_tmpl;
+  kp.P = P; kp.O = O; kp.Otot = pl.Otot; kp.HW = HW;
+  kp.PT = pl.PT; kp.OT = pl.OT; kp.n_ptiles = pl.n_ptiles; kp.n_otiles = pl.n_otiles;
+  kp.S = pl.S; kp.chunks_per_slab = pl.chunks_per_slab; kp.n_chunks = pl.n_chunks;
+  kp.ws = (int*)workspace; kp.cnt = pl.cnt;
+
+  auto aligned16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  const bool vec = (HW % 4 == 0) && aligned16(prop) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
+                   (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
+  dim3 grid(pl.S, B, pl.n_ptiles * pl.n_otiles);
+  if (vec)
+    mask_iou_partial_kernel<true><<<grid, kThreads, 0, st>>>(kp);
+  else
+    mask_iou_partial_kernel<false><<<grid, kThreads, 0, st>>>(kp);
+  int rc = check_launch();
+  if (rc) return rc;
+
+  FinParams fp;
+  fp.ws = (const int*)workspace; fp.S = pl.S; fp.cnt = pl.cnt; fp.B = B; fp.P = P; fp.O = O; fp.Otot = pl.Otot;
+  fp.n_prop = n_prop; fp.n_tmpl = n_tmpl; fp.iou = iou; fp.iou2 = iou2; fp.cos = cos; fp.w_cos = w_cos;
+  fp.w_iou = w_iou; fp.sim = sim; fp.counts = counts;
+  const long long total = (long long)B * pl.Otot * P;
+  int fblocks = (int)((total + 255) / 256);
+  if (fblocks > 8 * kNumSMs) fblocks = 8 * kNumSMs;
+  mask_iou_finalize_kernel<<<fblocks, 256, 0, st>>>(fp);
+  return check_launch();
+}
+
+extern "C" size_t dmm_mask_iou_rowwise_workspace_bytes(int N, int M) {
+  return dmm_mask_iou_workspace_bytes(N, 1, 1, M, 0);
+}
+
+extern "C" int dmm_mask_iou_rowwise(const float* a, const float* b, int N, int M, float* iou, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  // row i of a against row i of b == N problems with one proposal and one template each
+  if (N < 0 || M < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (N == 0) return DMM_OK;
+  if (!iou) return DMM_ERR_INVALID_ARGUMENT;
+  int done = 0;
+  while (done < N) {  // grid.y limit
+    const int nb = N - done < 65535 ? N - done : 65535;
+    int rc = dmm_mask_iou_pairwise(b + (long long)done * M, M, a + (long long)done * M, M, nullptr, 0, nb, 1, 1, M,
+                                   nullptr, nullptr, iou + done, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr,
+                                   workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    done += nb;
+  }
+  return DMM_OK;
+}

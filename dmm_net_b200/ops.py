@@ -1,0 +1,382 @@
+"""Batched tensor-level operators over the C ABI (include/dmm_b200.h), with autograd.
+
+PyTorch is only the plumbing here: device memory, the current CUDA stream, autograd bookkeeping.
+Every function takes CUDA fp32 tensors and launches hand-written sm_100a kernels from libdmm_b200.so;
+nothing falls back to torch ops or to the CPU.
+
+Batch convention: B independent (video, frame) problems of P proposals x O templates over H*W pixels;
+optional int32 ``n_prop[B]`` / ``n_tmpl[B]`` give the number of real rows per problem (rest is padding).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_VP = ctypes.c_void_p
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else _VP(t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return _VP(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"dmm_net_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _counts(t: Optional[torch.Tensor], B: int, dev) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = torch.as_tensor(t, device=dev).to(torch.int32).contiguous()
+    assert t.shape == (B,), t.shape
+    return t
+
+
+def pad_cols(P: int, O: int) -> int:
+    """Column stride of the [O x m] solver matrices: P <= O problems are padded to O+1 (match_model.py:109-113)."""
+    return max(P, O + 1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K1  mask IoU
+# ----------------------------------------------------------------------------------------------------------
+def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[torch.Tensor] = None,
+                      n_prop=None, n_tmpl=None, cos: Optional[torch.Tensor] = None, w_cos: float = 0.0,
+                      w_iou: float = 0.0, want_counts: bool = False):
+    """prop [B,P,...], tmpl [B,O,...] (trailing dims flattened to HW) -> dict(iou [B,O,P], iou2, sim, counts)."""
+    lib = _lib.load()
+    prop = _cuda_f32(prop, "prop")
+    tmpl = _cuda_f32(tmpl, "tmpl")
+    B, P = prop.shape[:2]
+    O = tmpl.shape[1]
+    prop = prop.reshape(B, P, -1)
+    tmpl = tmpl.reshape(B, O, -1)
+    HW = prop.shape[2]
+    assert tmpl.shape[0] == B and tmpl.shape[2] == HW, (prop.shape, tmpl.shape)
+    dev = prop.device
+    if tmpl2 is not None:
+        tmpl2 = _cuda_f32(tmpl2, "tmpl2").reshape(B, O, -1)
+        assert tmpl2.shape == tmpl.shape
+    n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
+    iou = torch.empty(B, O, P, device=dev)
+    iou2 = torch.empty(B, O, P, device=dev) if tmpl2 is not None else None
+    sim = None
+    if cos is not None:
+        cos = _cuda_f32(cos, "cos")
+        assert cos.shape == (B, O, P)
+        sim = torch.empty(B, O, P, device=dev)
+    counts = torch.empty(B, O * P + O + P, device=dev, dtype=torch.int32) if want_counts else None
+    out = {"iou": iou, "iou2": iou2, "sim": sim, "counts": counts}
+    if B == 0 or P == 0 or O == 0:
+        return out
+    step = 65535  # grid.y limit
+    for s in range(0, B, step):
+        e = min(B, s + step)
+        nb = e - s
+        ws_bytes = lib.dmm_mask_iou_workspace_bytes(nb, P, O, max(HW, 1), int(tmpl2 is not None))
+        ws = torch.empty(max(ws_bytes, 256), device=dev, dtype=torch.uint8)
+        sl = lambda t: None if t is None else t[s:e]
+        rc = lib.dmm_mask_iou_pairwise(_p(prop[s:e]), P * HW, _p(tmpl[s:e]), O * HW, _p(sl(tmpl2)), O * HW, nb, P, O, HW,
+                                       _p(sl(n_prop)), _p(sl(n_tmpl)), _p(iou[s:e]), _p(sl(iou2)), _p(sl(cos)),
+                                       float(w_cos), float(w_iou), _p(sl(sim)), _p(sl(counts)), _p(ws), ws.numel(),
+                                       _stream())
+        _lib.check(rc, "dmm_mask_iou_pairwise")
+    return out
+
+
+def mask_iou_rowwise(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a [N,M], b [N,M] -> iou [N]  (compute_iou_binary_mask_2D, match_helper.py:9-28)."""
+    lib = _lib.load()
+    a = _cuda_f32(a, "annotation")
+    b = _cuda_f32(b, "segmentation")
+    N, M = a.shape
+    out = torch.empty(N, device=a.device)
+    if N == 0:
+        return out
+    ws_bytes = lib.dmm_mask_iou_rowwise_workspace_bytes(N, max(M, 1))
+    ws = torch.empty(max(ws_bytes, 256), device=a.device, dtype=torch.uint8)
+    rc = lib.dmm_mask_iou_rowwise(_p(a), _p(b), N, M, _p(out), _p(ws), ws.numel(), _stream())
+    _lib.check(rc, "dmm_mask_iou_rowwise")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K2  cosine
+# ----------------------------------------------------------------------------------------------------------
+class _CosineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tmpl_feat, prop_feat, n_prop, n_tmpl, eps):
+        lib = _lib.load()
+        B, T, O, D = tmpl_feat.shape
+        P = prop_feat.shape[1]
+        cos = torch.empty(B, O, P, device=prop_feat.device)
+        if B * O * P > 0:
+            rc = lib.dmm_cosine_pairwise(_p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop), _p(n_tmpl),
+                                         float(eps), _p(cos), _stream())
+            _lib.check(rc, "dmm_cosine_pairwise")
+        ctx.save_for_backward(tmpl_feat, prop_feat, n_prop, n_tmpl)
+        ctx.eps = eps
+        return cos
+
+    @staticmethod
+    def backward(ctx, g_cos):
+        lib = _lib.load()
+        tmpl_feat, prop_feat, n_prop, n_tmpl = ctx.saved_tensors
+        B, T, O, D = tmpl_feat.shape
+        P = prop_feat.shape[1]
+        g_cos = g_cos.contiguous().float()
+        gq = torch.zeros_like(tmpl_feat)
+        gk = torch.zeros_like(prop_feat)
+        if B * O * P * D > 0:
+            rc = lib.dmm_cosine_pairwise_bwd(_p(g_cos), _p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop),
+                                             _p(n_tmpl), float(ctx.eps), _p(gq), _p(gk), _stream())
+            _lib.check(rc, "dmm_cosine_pairwise_bwd")
+        return gq, gk, None, None, None
+
+
+def cosine_pairwise(tmpl_feat: torch.Tensor, prop_feat: torch.Tensor, n_prop=None, n_tmpl=None, eps: float = 1e-8):
+    """tmpl_feat [B,T,O,D] (T template-feature sets), prop_feat [B,P,D] -> mean_t cos [B,O,P]; differentiable."""
+    tmpl_feat = _cuda_f32(tmpl_feat, "tmpl_feat")
+    prop_feat = _cuda_f32(prop_feat, "prop_feat")
+    B = prop_feat.shape[0]
+    assert tmpl_feat.dim() == 4 and prop_feat.dim() == 3 and tmpl_feat.shape[0] == B
+    assert tmpl_feat.shape[3] == prop_feat.shape[2], (tmpl_feat.shape, prop_feat.shape)
+    return _CosineFn.apply(tmpl_feat, prop_feat, _counts(n_prop, B, prop_feat.device),
+                           _counts(n_tmpl, B, prop_feat.device), eps)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K3  solver + head
+# ----------------------------------------------------------------------------------------------------------
+class _SolveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mat, score, n_prop, n_tmpl, max_iter, proj_iter, lr, negate, pad_rule, is_test, want_xlist):
+        lib = _lib.load()
+        B, O, P = mat.shape
+        MS = pad_cols(P, O) if pad_rule else P
+        dev = mat.device
+        new = lambda *s: torch.empty(*s, device=dev)
+        R, Xf, Bm, logic = new(B, O, MS), new(B, O, MS), new(B, O, MS), new(B, O, MS)
+        ms, ds = new(B, O), new(B, O)
+        n_list = torch.empty(B, device=dev, dtype=torch.int32)
+        xlist = new(B, max_iter + 1, O, MS) if want_xlist else None
+        cost = new(B, max_iter + 1) if want_xlist else None
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        saved = None
+        if need_grad:
+            saved = torch.empty(lib.dmm_relax_saved_bytes(B, max_iter, proj_iter), device=dev, dtype=torch.uint8)
+        if B * O > 0:
+            rc = lib.dmm_relax_solve(_p(mat), _p(score), B, P, O, _p(n_prop), _p(n_tmpl), max_iter, proj_iter, float(lr),
+                                     int(negate), int(pad_rule), int(is_test), _p(R), _p(Xf), _p(Bm), _p(logic), _p(ms),
+                                     _p(ds), _p(n_list), _p(xlist), _p(cost), _p(saved), _stream())
+            _lib.check(rc, "dmm_relax_solve")
+        ctx.save_for_backward(mat, score, R, logic, n_list, saved, n_prop, n_tmpl)
+        ctx.cfg = (max_iter, proj_iter, float(lr), int(negate), int(pad_rule))
+        ctx.mark_non_differentiable(logic, n_list)
+        if want_xlist:
+            ctx.mark_non_differentiable(xlist, cost)
+            return R, Bm, ms, ds, Xf, logic, n_list, xlist, cost
+        return R, Bm, ms, ds, Xf, logic, n_list
+
+    @staticmethod
+    def backward(ctx, gR, gBm, gms, gds, gXf, *unused):
+        lib = _lib.load()
+        mat, score, R, logic, n_list, saved, n_prop, n_tmpl = ctx.saved_tensors
+        max_iter, proj_iter, lr, negate, pad_rule = ctx.cfg
+        B, O, P = mat.shape
+        c = lambda g: None if g is None else g.contiguous().float()
+        gR, gBm, gms, gds, gXf = c(gR), c(gBm), c(gms), c(gds), c(gXf)
+        g_mat = torch.zeros_like(mat)
+        g_score = torch.zeros_like(score) if score is not None else None
+        if saved is None:
+            raise RuntimeError("dmm_relax_solve: backward requested but the forward ran without grad inputs")
+        if B * O * P > 0:
+            rc = lib.dmm_relax_solve_bwd(_p(gR), _p(gXf), _p(gBm), _p(gms), _p(gds), _p(mat), _p(score), _p(R), _p(logic),
+                                         _p(n_list), _p(saved), B, P, O, _p(n_prop), _p(n_tmpl), max_iter, proj_iter,
+                                         lr, negate, pad_rule, _p(g_mat), _p(g_score), _stream())
+            _lib.check(rc, "dmm_relax_solve_bwd")
+        return g_mat, g_score, None, None, None, None, None, None, None, None, None
+
+
+def relax_solve(mat: torch.Tensor, score: Optional[torch.Tensor] = None, n_prop=None, n_tmpl=None,
+                max_iter: int = 20, proj_iter: int = 5, lr: float = 0.1, negate: bool = True, pad_rule: bool = True,
+                is_test: bool = True, want_xlist: bool = False):
+    """mat [B,O,P] (similarity when negate else cost) -> (R, Bmat, match_score, det_score, X_final, logic, n_list[, xlist, cost])."""
+    mat = _cuda_f32(mat, "mat")
+    B = mat.shape[0]
+    if score is not None:
+        score = _cuda_f32(score, "prop_score")
+        assert score.shape == (B, mat.shape[2]), (score.shape, mat.shape)
+    dev = mat.device
+    return _SolveFn.apply(mat, score, _counts(n_prop, B, dev), _counts(n_tmpl, B, dev), int(max_iter), int(proj_iter),
+                          float(lr), bool(negate), bool(pad_rule), bool(is_test), bool(want_xlist))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K4  assignment apply
+# ----------------------------------------------------------------------------------------------------------
+class _ApplyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Bm, prop, logic, n_prop, n_tmpl, row_map, O_out, zero_fill):
+        lib = _lib.load()
+        B, O, MS = Bm.shape
+        P, HW = prop.shape[1], prop.shape[2]
+        out = torch.empty(B, O_out, HW, device=prop.device)
+        if B * O_out * HW > 0:
+            rc = lib.dmm_assign_apply(_p(Bm), _p(prop), P * HW, B, P, O, MS, HW, _p(n_prop), _p(n_tmpl), _p(row_map),
+                                      O_out, int(zero_fill), _p(out), O_out * HW, _stream())
+            _lib.check(rc, "dmm_assign_apply")
+        ctx.save_for_backward(Bm, prop, logic, n_prop, n_tmpl, row_map)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        Bm, prop, logic, n_prop, n_tmpl, row_map = ctx.saved_tensors
+        B, O, MS = Bm.shape
+        P, HW = prop.shape[1], prop.shape[2]
+        g_out = g_out.contiguous().float()
+        O_out = g_out.shape[1]
+        gB = torch.zeros_like(Bm) if ctx.needs_input_grad[0] else None
+        gprop = torch.zeros_like(prop) if ctx.needs_input_grad[1] else None
+        if B * O * P * HW > 0 and (gB is not None or gprop is not None):
+            ws = torch.empty(lib.dmm_assign_apply_bwd_workspace_bytes(B, P, O, HW), device=prop.device, dtype=torch.uint8)
+            sel = logic if logic is not None else (Bm != 0).float()
+            rc = lib.dmm_assign_apply_bwd(_p(g_out), O_out * HW, _p(prop), P * HW, _p(Bm), _p(sel), B, P, O, MS, HW,
+                                          _p(n_prop), _p(n_tmpl), _p(row_map), _p(gB), _p(gprop), _p(ws), ws.numel(),
+                                          _stream())
+            _lib.check(rc, "dmm_assign_apply_bwd")
+        return gB, gprop, None, None, None, None, None, None
+
+
+def assign_apply(Bm: torch.Tensor, prop: torch.Tensor, logic: Optional[torch.Tensor] = None, n_prop=None, n_tmpl=None,
+                 row_map: Optional[torch.Tensor] = None, O_out: Optional[int] = None, zero_fill: bool = True):
+    """Bmat [B,O,MS] x prop [B,P,HW] -> out [B,O_out,HW]; row o of problem b lands in row row_map[b,o].
+    ``logic`` (the solver's selection mask) restricts the gradient w.r.t. Bmat to the selected entries, exactly the
+    entries through which the reference's ``R * logic_mask`` lets gradient flow."""
+    Bm = _cuda_f32(Bm, "Bmat")
+    prop = _cuda_f32(prop, "prop")
+    B, O, MS = Bm.shape
+    prop = prop.reshape(B, prop.shape[1], -1)
+    dev = prop.device
+    if row_map is not None:
+        row_map = torch.as_tensor(row_map, device=dev).to(torch.int32).contiguous()
+        assert row_map.shape == (B, O)
+    if O_out is None:
+        O_out = O
+    if logic is not None:
+        logic = _cuda_f32(logic, "logic")
+    return _ApplyFn.apply(Bm, prop, logic, _counts(n_prop, B, dev), _counts(n_tmpl, B, dev), row_map, int(O_out),
+                          bool(zero_fill))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K5  ROI mean pooling
+# ----------------------------------------------------------------------------------------------------------
+class _RoiPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rois, *feats):
+        lib = _lib.load()
+        N, C = feats[0].shape[:2]
+        R = rois.shape[0]
+        out = torch.empty(R, 4 * C, device=rois.device)
+        Hl = (ctypes.c_int * 4)(*[f.shape[2] for f in feats])
+        Wl = (ctypes.c_int * 4)(*[f.shape[3] for f in feats])
+        ptrs = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in feats])
+        if R * C > 0:
+            rc = lib.dmm_roi_mean_pool(ptrs, Hl, Wl, N, C, _p(rois), R, _p(out), _stream())
+            _lib.check(rc, "dmm_roi_mean_pool")
+        ctx.save_for_backward(rois)
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        (rois,) = ctx.saved_tensors
+        shapes = ctx.shapes
+        N, C = shapes[0][:2]
+        R = rois.shape[0]
+        g_out = g_out.contiguous().float()
+        gf = [torch.zeros(s, device=rois.device) for s in shapes]
+        Hl = (ctypes.c_int * 4)(*[s[2] for s in shapes])
+        Wl = (ctypes.c_int * 4)(*[s[3] for s in shapes])
+        ptrs = (ctypes.c_void_p * 4)(*[g.data_ptr() for g in gf])
+        if R * C > 0:
+            rc = lib.dmm_roi_mean_pool_bwd(_p(g_out), Hl, Wl, N, C, _p(rois), R, ptrs, _stream())
+            _lib.check(rc, "dmm_roi_mean_pool_bwd")
+        return (None, *gf)
+
+
+def roi_mean_pool(features: Sequence[torch.Tensor], rois: torch.Tensor) -> torch.Tensor:
+    """4 levels [N,C,Hl,Wl] at strides 4/8/16/32, rois [R,5] = (batch idx, x1, y1, x2, y2) -> [R, 4*C]."""
+    assert len(features) == 4, "FeatureExtractor pools 4 levels (feature_extractor.py:13)"
+    feats = [_cuda_f32(f, "feature") for f in features]
+    N, C = feats[0].shape[:2]
+    for f in feats:
+        assert f.dim() == 4 and f.shape[0] == N and f.shape[1] == C, [tuple(g.shape) for g in feats]
+    rois = _cuda_f32(rois, "rois")
+    assert rois.dim() == 2 and rois.shape[1] == 5, rois.shape
+    return _RoiPoolFn.apply(rois, *feats)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the fused layer over a batch of problems
+# ----------------------------------------------------------------------------------------------------------
+def match_batch(prop_feat: torch.Tensor, prop_mask: torch.Tensor, tmpl_feat: torch.Tensor, tmpl_mask: torch.Tensor,
+                prop_score: torch.Tensor, targets: Optional[torch.Tensor] = None, *, max_iter: int, proj_iter: int,
+                lr: float, score_weight: float, is_test: bool, n_prop=None, n_tmpl=None, row_map=None,
+                O_out: Optional[int] = None, apply: bool = True):
+    """MatchModel.forward for B problems in five launches (cosine, IoU, IoU-finalize+mix, solve+head, apply).
+
+    prop_feat [B,P,D], prop_mask [B,P,H,W], tmpl_feat [B,T,O,D] (or [B,O,D]), tmpl_mask [B,O,H,W], prop_score [B,P],
+    targets [B,O,H,W] or None.  Returns dict(full_outmask [B,O_out,H,W], match_score, det_score [B,O], sim, R, Bmat,
+    logic, n_list, cost_loss [B] or None).
+    """
+    if tmpl_feat.dim() == 3:
+        tmpl_feat = tmpl_feat.unsqueeze(1)
+    B, P = prop_mask.shape[:2]
+    O = tmpl_mask.shape[1]
+    H, W = prop_mask.shape[-2:]
+    dev = prop_mask.device
+    n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
+    cos = cosine_pairwise(tmpl_feat, prop_feat, n_prop, n_tmpl)                       # K2
+    w = float(score_weight)
+    if torch.is_grad_enabled() and cos.requires_grad:
+        r = mask_iou_pairwise(prop_mask, tmpl_mask, targets, n_prop, n_tmpl)           # K1 (both template sets in one pass)
+        # sim = cos*(1-w) + iou*w with separate fp32 roundings (match_model.py:90); kept in torch here so that
+        # autograd sees cos.  IoU carries no gradient (match_helper.py:20 runs under no_grad).
+        sim = cos * (1 - w) + r["iou"] * w
+    else:
+        r = mask_iou_pairwise(prop_mask, tmpl_mask, targets, n_prop, n_tmpl, cos=cos, w_cos=1 - w, w_iou=w)
+        sim = r["sim"]                                                                 # mixed in K1's finalize kernel
+    cost_loss = None
+    if targets is not None:
+        gt = relax_solve(r["iou2"], None, n_prop, n_tmpl, 0, 0, 0.0, True, False, True)[0]   # greedy one-hot (match_helper.py:44)
+        d2 = (cos - gt) ** 2
+        if n_prop is None and n_tmpl is None:
+            cost_loss = d2.mean(dim=(1, 2))                                           # F.mse_loss per problem
+        else:
+            npv = n_prop if n_prop is not None else torch.full((B,), P, device=dev, dtype=torch.int32)
+            ntv = n_tmpl if n_tmpl is not None else torch.full((B,), O, device=dev, dtype=torch.int32)
+            valid = (torch.arange(P, device=dev)[None, None, :] < npv[:, None, None]) & \
+                    (torch.arange(O, device=dev)[None, :, None] < ntv[:, None, None])
+            cost_loss = (d2 * valid).sum(dim=(1, 2)) / (npv * ntv).clamp(min=1).float()
+    R, Bm, ms, ds, Xf, logic, n_list = relax_solve(sim, prop_score, n_prop, n_tmpl, max_iter, proj_iter, lr, True, True,
+                                                   is_test)                            # K3
+    full = None
+    if apply:
+        full = assign_apply(Bm, prop_mask, logic, n_prop, n_tmpl, row_map, O_out).view(B, -1, H, W)   # K4
+    return {"full_outmask": full, "match_score": ms, "det_score": ds, "sim": sim, "R": R, "Bmat": Bm, "logic": logic,
+            "n_list": n_list, "cost_loss": cost_loss, "cos": cos, "iou": r["iou"], "X_final": Xf}

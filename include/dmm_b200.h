@@ -1,0 +1,145 @@
+/*
+ * dmm_b200.h -- C ABI of libdmm_b200.so: the sm_100a kernels behind DMM-Net's matching layer.
+ *
+ * Drop-in boundary.  The reference has no native code; what a maintainer binds
+ * instead of the torch op sequences below is this library (ctypes stub: INTEGRATION.md).
+ * Every entry point
+ *   - takes raw DEVICE pointers, explicit sizes/strides, scalars and a CUDA stream (cudaStream_t cast to void*);
+ *   - allocates nothing the caller can see (workspace is passed in, size from the *_workspace_bytes query);
+ *   - is asynchronous on `stream`, re-entrant, keeps no global mutable state;
+ *   - returns 0 on success or a DMM_ERR_* code (no exceptions).  Python keeps the reference's AssertionError
+ *     shape checks (dmm/utils/checker.py) above this ABI.
+ *
+ * Shapes use the reference's names: P proposals, O templates, H*W = HW pixels, D feature channels,
+ * B independent (video, frame) problems per launch.  All tensors are dense row-major fp32 unless noted.
+ * Optional per-problem counts n_prop[B] / n_tmpl[B] (device int32, may be NULL) say how many of the P / O
+ * rows of problem b are real; the rest is padding (dmm_model.py:117-125 selects the first O valid templates).
+ * MS = max(P, O+1) is the column stride of every [O x m] solver matrix: problems with P <= O are padded with
+ * zero-similarity dummy proposals to O+1 columns (match_model.py:109-113).
+ */
+#ifndef DMM_B200_H_
+#define DMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMM_B200_VERSION 0x000100 /* 0.1.0 */
+
+enum {
+  DMM_OK = 0,
+  DMM_ERR_INVALID_ARGUMENT = 1, /* NULL where data is required, negative size, misuse */
+  DMM_ERR_UNSUPPORTED_SHAPE = 2, /* beyond the compiled limits (see dmm_b200_limits) */
+  DMM_ERR_WORKSPACE_TOO_SMALL = 3,
+  DMM_ERR_CUDA = 4 /* a CUDA runtime call failed; dmm_b200_last_cuda_error() has the cudaError_t */
+};
+
+/* ---- library queries -------------------------------------------------------------------------------- */
+int dmm_b200_version(void);                 /* DMM_B200_VERSION */
+const char* dmm_b200_arch(void);            /* "sm_100a" */
+const char* dmm_b200_error_string(int code);
+int dmm_b200_last_cuda_error(void);         /* thread-local cudaError_t of the last DMM_ERR_CUDA */
+/* out[0]=max O per solver problem, out[1]=max padded columns m per solver problem, out[2]=max D, out[3]=SM count used for grid sizing (0 if no device) */
+int dmm_b200_limits(int* out4);
+
+/* ---- K1: pairwise binary-mask IoU ---------------------------------------------------------------------
+ * Replaces compute_iou_binary_mask_2D on the expanded [O*P, HW] pairs (match_helper.py:9-28 called from
+ * match_model.py:83-89) and, with tmpl2 = targets, the second IoU build of compute_matching_loss
+ * (match_helper.py:30-42) in the same pass over the proposals.
+ *   iou[b,o,p] = |A_o & B_p| / (float(|A_o | B_p|) + 1e-6f),   bits = (mask > 0.5f)      -- bit-exact
+ * prop [B][P][HW] (batch stride prop_bstride elements), tmpl [B][O][HW], tmpl2 optional (NULL) [B][O][HW].
+ * Outputs (each may be NULL): iou/iou2 [B][O][P]; sim [B][O][P] = cos*w_cos + iou*w_iou (match_model.py:90,
+ * separate fp32 roundings, no FMA) when cos != NULL; counts [B][3 slots] see below.
+ * counts (optional, int32): [B][O*P + O + P] = inter[o][p], area_tmpl[o], area_prop[p] for the FIRST template set.
+ */
+size_t dmm_mask_iou_workspace_bytes(int B, int P, int O, int HW, int two_template_sets);
+int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, const float* tmpl, long long tmpl_bstride,
+                          const float* tmpl2, long long tmpl2_bstride, int B, int P, int O, int HW,
+                          const int* n_prop, const int* n_tmpl, float* iou, float* iou2, const float* cos,
+                          float w_cos, float w_iou, float* sim, int* counts, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Row-paired IoU: a[N][M] vs b[N][M] -> iou[N]  (compute_iou_binary_mask_2D itself; callers trainer.py:190,298). */
+size_t dmm_mask_iou_rowwise_workspace_bytes(int N, int M);
+int dmm_mask_iou_rowwise(const float* a, const float* b, int N, int M, float* iou, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- K2: pairwise cosine ------------------------------------------------------------------------------
+ * Replaces get_cosine_score (match_helper.py:51-64) averaged over the T template-feature sets
+ * (match_model.py:72-76).  tmpl_feat [B][T][O][D], prop_feat [B][P][D] -> cos [B][O][P].
+ * cos_t[o,p] = <q,k> / (max(|q|,eps) * max(|k|,eps)), eps = 1e-8 (F.cosine_similarity).
+ */
+int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
+                        const int* n_prop, const int* n_tmpl, float eps, float* cos, void* stream);
+/* d(loss)/d(features) from g_cos [B][O][P]; g_tmpl_feat [B][T][O][D], g_prop_feat [B][P][D] are overwritten. */
+int dmm_cosine_pairwise_bwd(const float* g_cos, const float* tmpl_feat, const float* prop_feat, int B, int T,
+                            int P, int O, int D, const int* n_prop, const int* n_tmpl, float eps,
+                            float* g_tmpl_feat, float* g_prop_feat, void* stream);
+
+/* ---- K3: relaxed matching solver + assignment head ----------------------------------------------------
+ * Replaces relax_matching (relax_match.py:36-105: greedy init, gradient step, Dykstra sweeps over
+ * {X>=0} n {col sums<=1} n {row sums==1}, both exact-equality early exits) and the [O x m] part of
+ * match_with_first_frame (match_model.py:109-130,146-147): zero-column padding when P<=O, C=-sim,
+ * R = mean of the PRE-projection iterates, logic = (R==rowmax) [is_test] or (R>0.01), Bmat = R*logic,
+ * match_score = max_p(clamp(R,0,1)*sim), det_score = sum_p score_p*Bmat.
+ * One warp per problem; X, the three Dykstra increments, C and the running sum of iterates stay in registers.
+ *
+ * in : mat [B][O][P]  (a similarity if negate!=0, else used as the cost C directly), prop_score [B][P] or NULL
+ * out: (any may be NULL)  R, X_final, Bmat, logic [B][O][MS];  match_score, det_score [B][O];
+ *      n_list [B] = len(X_list) = 1 + outer steps run;
+ *      xlist [B][max_iter+1][O][MS] every recorded iterate, cost [B][max_iter+1] (cost[0]=0) -- the
+ *      free-function API returns them (relax_match.py:105);
+ *      saved: opaque forward state for dmm_relax_solve_bwd, dmm_relax_saved_bytes(B,max_iter,proj_iter) bytes.
+ * pad_to_square_plus_one: apply the P<=O padding rule (the layer does; the free function does not).
+ */
+size_t dmm_relax_saved_bytes(int B, int max_iter, int proj_iter);
+int dmm_relax_solve(const float* mat, const float* prop_score, int B, int P, int O, const int* n_prop,
+                    const int* n_tmpl, int max_iter, int proj_iter, float lr, int negate, int pad_rule,
+                    int is_test, float* R, float* X_final, float* Bmat, float* logic, float* match_score,
+                    float* det_score, int* n_list, float* xlist, float* cost, void* saved, void* stream);
+/* Backward of the above w.r.t. `mat` and prop_score.  Cotangents (any may be NULL): g_R, g_Xfinal, g_Bmat [B][O][MS],
+ * g_match_score, g_det_score [B][O].  Needs the forward's R, logic, mat, prop_score, n_list and `saved`.
+ * Outputs: g_mat [B][O][P] (overwritten), g_prop_score [B][P] (overwritten, may be NULL). */
+int dmm_relax_solve_bwd(const float* g_R, const float* g_Xfinal, const float* g_Bmat, const float* g_match_score,
+                        const float* g_det_score, const float* mat, const float* prop_score, const float* R,
+                        const float* logic, const int* n_list, const void* saved, int B, int P, int O,
+                        const int* n_prop, const int* n_tmpl, int max_iter, int proj_iter, float lr, int negate,
+                        int pad_rule, float* g_mat, float* g_prop_score, void* stream);
+
+/* ---- K4: assignment apply -----------------------------------------------------------------------------
+ * Replaces full_outmask = torch.mm(binary_Ridx_matched, proposed_mask2d) (match_model.py:144) and, with
+ * row_map, the valid-row scatter torch.mm(FO_matrix, .) of dmm_model.py:133-135.
+ * Bmat [B][O][MS] (columns >= P are padding and multiply zero rows), prop [B][P][HW] -> out [B][O_out][HW];
+ * row o of problem b goes to output row row_map[b*O+o] (identity when row_map==NULL); when zero_fill!=0 every
+ * output row not produced is written with zeros.  Only the non-zero coefficients are streamed.
+ */
+int dmm_assign_apply(const float* Bmat, const float* prop, long long prop_bstride, int B, int P, int O, int MS,
+                     int HW, const int* n_prop, const int* n_tmpl, const int* row_map, int O_out, int zero_fill,
+                     float* out, long long out_bstride, void* stream);
+/* g_Bmat[b,o,p] = <g_out[b,row(o),:], prop[b,p,:]> for the entries selected by `logic` (others 0);
+ * optional g_prop [B][P][HW] = Bmat^T g_out (overwritten) when the proposal masks need a gradient. */
+size_t dmm_assign_apply_bwd_workspace_bytes(int B, int P, int O, int HW);
+int dmm_assign_apply_bwd(const float* g_out, long long gout_bstride, const float* prop, long long prop_bstride,
+                         const float* Bmat, const float* logic, int B, int P, int O, int MS, int HW,
+                         const int* n_prop, const int* n_tmpl, const int* row_map, float* g_Bmat, float* g_prop,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5: ROI mean pooling -----------------------------------------------------------------------------
+ * Replaces FeatureExtractor.forward (feature_extractor.py:20-52): legacy ROIAlign(14x14, sampling_ratio 2,
+ * scales 1/4..1/32) on each of 4 levels followed by the spatial mean, i.e. the separable contraction
+ *   out[r, l*C + c] = sum_y sum_x wy[r,l,y] * wx[r,l,x] * F_l[b_r, c, y, x].
+ * feat[l] is [N][C][Hl][Wl]; rois [R][5] = (batch index, x1, y1, x2, y2) in image pixels; out [R][4*C].
+ */
+int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], const int Wl[4], int N, int C,
+                      const float* rois, int R, float* out, void* stream);
+/* g_feat[l] [N][C][Hl][Wl] must be zero-initialised by the caller; gradients are accumulated with atomics. */
+int dmm_roi_mean_pool_bwd(const float* g_out, const int Hl[4], const int Wl[4], int N, int C, const float* rois,
+                          int R, float* const g_feat[4], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMM_B200_H_ */

@@ -1,0 +1,272 @@
+"""GPU parity: the CUDA path (through the C ABI) against (a) the golden vectors produced by the unmodified
+reference and (b) the CPU oracle on fresh seeded inputs.  Integer work (IoU) must be bit-exact; float paths are
+held to 1e-4 (BASELINE.json north_star) -- in practice ~1e-6 -- and the row-argmax of the assignment must be equal."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import T, golden_names, load_golden
+from dmm_net_b200 import ops
+from dmm_net_b200.modules.match_model import MatchModel
+from dmm_net_b200.modules.submodules.relax_match import relax_matching
+from dmm_net_b200.synth import default_cfg, make_problem, make_problems
+from dmm_net_b200.utils import match_helper
+from oracle import match_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4
+
+
+def close(a, b, tol=TOL, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = float(np.abs(a - b).max()) if a.size else 0.0
+    assert err <= tol, f"{what}: max abs err {err:.3e} > {tol}"
+    return err
+
+
+# ---------------------------------------------------------------------------------------------------------
+# golden vectors from the reference
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("layer_"))
+def test_layer_against_reference_golden(name):
+    g = load_golden(name)
+    P, O, H, W, D, mi, pi, is_test = [int(v) for v in g["meta"]]
+    cfg = default_cfg(mi, pi, float(g["lr"]), float(g["score_weight"]))
+    layer = MatchModel(cfg, is_test=is_test)
+    pf = T(g["prop_feat"], DEV).requires_grad_(not is_test)
+    tf = T(g["tmpl_feat"], DEV).requires_grad_(not is_test)
+    sc = T(g["prop_score"], DEV).requires_grad_(not is_test)
+    pm, tm = T(g["prop_mask"], DEV), T(g["tmpl_mask"], DEV)
+    tg = T(g["targets"], DEV) if "targets" in g else None
+
+    iou = ops.mask_iou_pairwise(pm[None], tm[None])["iou"][0]
+    np.testing.assert_array_equal(iou.cpu().numpy(), g["iou"])                      # bit-exact
+    close(match_helper.get_cosine_score(tf, pf), g["cos"], 2e-6, "cos")
+    with torch.set_grad_enabled(not is_test):
+        sim, n_prop, n_tplt, _ = layer.compute_cost_matrix({"proposed": pf, "template": [tf]},
+                                                           {"proposed": pm, "template": tm}, {"proposal_score": sc}, tg)
+        assert (n_prop, n_tplt) == (P, O)
+        close(sim, g["sim"], 2e-6, "sim")
+        _, _, _, logic, bmat = layer.match_with_first_frame(sim, P, O, pm, sc, tm)
+        close(bmat, g["bmat"], TOL, "bmat")
+        np.testing.assert_array_equal(logic.cpu().numpy(), g["logic"])               # same selected entries
+        full, ms, ds, full2, loss = layer(pf, pm, [tf], tm, sc, tg)
+    assert full is full2
+    close(full, g["full_outmask"], TOL, "full_outmask")
+    close(ms, g["match_score"], TOL, "match_score")
+    close(ds, g["det_score"], TOL, "det_score")
+    assert np.array_equal(bmat.argmax(1).cpu().numpy(), g["bmat"].argmax(1))         # assignment argmax bit-exact
+    if "cost_loss" in g:
+        close(loss["cost_loss"], g["cost_loss"], 1e-6, "cost_loss")
+    else:
+        assert loss == {}
+    if not is_test:
+        total = (full * T(g["w_mask"], DEV)).sum() + (ms * T(g["w_ms"], DEV)).sum() + (ds * T(g["w_ds"], DEV)).sum()
+        if "cost_loss" in loss:
+            total = total + 3.0 * loss["cost_loss"]
+        total.backward()
+        scale = max(1.0, float(np.abs(g["g_prop_feat"]).max()))
+        close(pf.grad, g["g_prop_feat"], TOL * scale, "d/d prop_feat")
+        close(tf.grad, g["g_tmpl_feat"], TOL * max(1.0, float(np.abs(g["g_tmpl_feat"]).max())), "d/d tmpl_feat")
+        close(sc.grad, g["g_prop_score"], TOL * max(1.0, float(np.abs(g["g_prop_score"]).max())), "d/d prop_score")
+
+
+@pytest.mark.parametrize("name", golden_names("solver_"))
+def test_solver_against_reference_golden(name):
+    g = load_golden(name)
+    mi, pi = [int(v) for v in g["params"]]
+    C = T(g["C"], DEV)
+    n, m = C.shape
+    if n > 16 or m > 128 or (n > 8 and m > 64):
+        pytest.skip("beyond the register-tile limits (dmm_b200_limits)")
+    X, cost, X_list, _ = relax_matching(C, max_iter=mi, proj_iter=pi, lr=float(g["lr"]))
+    np.testing.assert_array_equal(X_list[0].cpu().numpy(), g["X0"])                  # greedy start bit-exact
+    if name in ("solver_16x64_default", "solver_7x33_longrun"):
+        # hundreds of outer steps: the exact-equality exit can move by a few steps with fp32 summation order
+        assert abs(len(X_list) - int(g["n_list"])) <= max(3, int(g["n_list"]) // 20)
+    else:
+        assert len(X_list) == int(g["n_list"])                                       # both exits fire at the same step
+        assert len(cost) == len(g["cost"])
+        close(np.array(cost), g["cost"], 1e-4, "cost")
+    R = sum(X_list) / len(X_list)
+    close(R, g["R"], TOL, "mean of iterates")
+    close(X, g["X"], 5e-4 if mi > 100 else TOL, "final X")
+    assert np.array_equal(R.argmax(1).cpu().numpy(), g["R"].argmax(1))
+    R2 = ops.relax_solve(C[None], None, max_iter=mi, proj_iter=pi, lr=float(g["lr"]), negate=False, pad_rule=False)[0][0]
+    close(R2, R, 1e-6, "R from kernel vs mean(xlist)")
+
+
+def test_solver_known_answer():
+    """relax_match.py:108-119: the relaxed solution of the 3x3 cost equals SciPy's Hungarian assignment."""
+    C = torch.tensor([[4., 1, 3], [2, 0, 5], [3, 2, 2]], device=DEV)
+    X, cost, X_list, _ = relax_matching(C, max_iter=100, proj_iter=100, lr=0.1)
+    want = torch.tensor([[0., 1, 0], [1, 0, 0], [0, 0, 1]], device=DEV)
+    assert (X - want).abs().max() < 1e-3
+    assert torch.equal(orc.hungarian_onehot(C.cpu()), want.cpu())
+    assert len(X_list) == 58
+
+
+def test_rowwise_iou_golden_and_edges():
+    g = load_golden("iou_rows")
+    got = match_helper.compute_iou_binary_mask_2D(T(g["a"], DEV), T(g["b"], DEV))
+    np.testing.assert_array_equal(got.cpu().numpy(), g["iou"])
+    with pytest.raises(AssertionError):
+        match_helper.compute_iou_binary_mask_2D(torch.zeros(2, 3, 4, device=DEV), torch.zeros(2, 3, 4, device=DEV))
+    e = match_helper.compute_iou_binary_mask_2D(torch.zeros(0, 7, device=DEV), torch.zeros(0, 7, device=DEV))
+    assert e.shape == (0,)
+
+
+def test_cosine_golden():
+    g = load_golden("cosine")
+    close(match_helper.get_cosine_score(T(g["q"], DEV), T(g["k"], DEV)), g["cos"], 2e-6, "cos")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fresh seeded inputs against the CPU oracle
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P,O,H,W", [(50, 10, 64, 112), (7, 2, 19, 23), (33, 16, 8, 40), (70, 5, 16, 16),
+                                      (100, 12, 12, 20), (1, 1, 5, 5), (64, 16, 30, 34)])
+def test_pairwise_iou_shapes_bit_exact(P, O, H, W):
+    pr = make_problems(3, P, O, H, W, 8, seed=P * 131 + O, with_targets=True)
+    d = pr.to(DEV)
+    r = ops.mask_iou_pairwise(d.prop_mask, d.tmpl_mask, d.targets, want_counts=True)
+    for b in range(3):
+        want = orc.pairwise_binary_iou(pr.prop_mask[b].view(P, -1), pr.tmpl_mask[b].view(O, -1), expand=False)
+        np.testing.assert_array_equal(r["iou"][b].cpu().numpy(), want.numpy())
+        want2 = orc.pairwise_binary_iou(pr.prop_mask[b].view(P, -1), pr.targets[b].view(O, -1), expand=False)
+        np.testing.assert_array_equal(r["iou2"][b].cpu().numpy(), want2.numpy())
+        cnt = r["counts"][b].cpu()
+        assert torch.equal(cnt[O * P + O:], (pr.prop_mask[b].view(P, -1) > 0.5).sum(1).int())
+        assert torch.equal(cnt[O * P:O * P + O], (pr.tmpl_mask[b].view(O, -1) > 0.5).sum(1).int())
+
+
+def test_pairwise_iou_unaligned_views():
+    """rows that are not 16-byte aligned take the scalar-load kernel; the result must not change."""
+    pr = make_problems(2, 9, 3, 11, 13, 8, seed=5)
+    buf = torch.zeros(2 * 9 * 143 + 1, device=DEV)
+    pm = buf[1:].view(2, 9, 143)
+    pm.copy_(pr.prop_mask.view(2, 9, 143))
+    tm = pr.tmpl_mask.to(DEV)
+    assert pm.data_ptr() % 16 != 0
+    lib_iou = ops.mask_iou_pairwise(pm, tm)["iou"]          # _cuda_f32 keeps the storage offset (already contiguous)
+    for b in range(2):
+        want = orc.pairwise_binary_iou(pr.prop_mask[b].view(9, -1), pr.tmpl_mask[b].view(3, -1), expand=False)
+        np.testing.assert_array_equal(lib_iou[b].cpu().numpy(), want.numpy())
+
+
+@pytest.mark.parametrize("is_test", [1, 0])
+def test_batched_layer_with_ragged_counts(is_test):
+    """B problems in one launch with per-problem row counts == the oracle run problem by problem on the sliced inputs."""
+    B, P, O, H, W, D = 6, 20, 5, 24, 40, 64
+    pr = make_problems(B, P, O, H, W, D, seed=99, with_targets=not is_test)
+    n_prop = torch.tensor([20, 13, 5, 3, 20, 1])
+    n_tmpl = torch.tensor([5, 2, 5, 4, 1, 3])
+    cfg = default_cfg(10 if not is_test else 20, 5)
+    layer = MatchModel(cfg, is_test=is_test)
+    d = pr.to(DEV)
+    with torch.no_grad():
+        out = layer.forward_many(d.prop_feat, d.prop_mask, d.tmpl_feat, d.tmpl_mask, d.prop_score, d.targets,
+                                 n_prop=n_prop, n_tmpl=n_tmpl)
+    for b in range(B):
+        p, o = int(n_prop[b]), int(n_tmpl[b])
+        tg = None if pr.targets is None else pr.targets[b, :o]
+        full, ms, ds, _, loss = orc.match_layer_forward(cfg, is_test, pr.prop_feat[b, :p], pr.prop_mask[b, :p],
+                                                        [pr.tmpl_feat[b, :o]], pr.tmpl_mask[b, :o], pr.prop_score[b, :p], tg)
+        close(out["full_outmask"][b, :o], full, TOL, f"full_outmask[{b}]")
+        assert out["full_outmask"][b, o:].abs().max().item() == 0 if o < O else True
+        close(out["match_score"][b, :o], ms, TOL, f"match_score[{b}]")
+        close(out["det_score"][b, :o], ds, TOL, f"det_score[{b}]")
+        if tg is not None:
+            close(out["cost_loss"][b], loss["cost_loss"], 1e-6, f"cost_loss[{b}]")
+
+
+def test_row_map_scatter_equals_container():
+    """row_map fuses dmm_model.py:133-135 (scatter of the O valid rows into F slots) into the apply kernel."""
+    B, P, O, F, H, W, D = 3, 12, 3, 5, 16, 24, 32
+    pr = make_problems(B, P, O, H, W, D, seed=7)
+    d = pr.to(DEV)
+    cfg = default_cfg(20, 5)
+    layer = MatchModel(cfg, is_test=1)
+    row_map = torch.tensor([[0, 1, 2], [4, 0, 2], [1, 3, 4]])
+    with torch.no_grad():
+        out = layer.forward_many(d.prop_feat, d.prop_mask, d.tmpl_feat, d.tmpl_mask, d.prop_score, row_map=row_map, out_rows=F)
+        ref = layer.forward_many(d.prop_feat, d.prop_mask, d.tmpl_feat, d.tmpl_mask, d.prop_score)
+    full = out["full_outmask"]
+    assert full.shape == (B, F, H, W)
+    for b in range(B):
+        used = set(row_map[b].tolist())
+        for o in range(O):
+            assert torch.equal(full[b, row_map[b, o]], ref["full_outmask"][b, o])
+        for f in range(F):
+            if f not in used:
+                assert full[b, f].abs().max().item() == 0
+
+
+def test_gradients_match_oracle_autograd():
+    """Backward of cosine, solver (Dykstra sweeps reversed from saved bit masks), head and apply vs autograd on the oracle."""
+    P, O, H, W, D = 17, 4, 20, 28, 48
+    pr = make_problem(P, O, H, W, D, config=3, index=1, with_targets=True)
+    cfg = default_cfg(10, 5)
+    gen = torch.Generator().manual_seed(1)
+    w_mask, w_ms, w_ds = torch.rand(O, H, W, generator=gen), torch.rand(O, generator=gen), torch.rand(O, generator=gen)
+
+    def run(mod_forward, dev):
+        pf = pr.prop_feat.to(dev).requires_grad_(True)
+        tf = pr.tmpl_feat.to(dev).requires_grad_(True)
+        sc = pr.prop_score.to(dev).requires_grad_(True)
+        pm = pr.prop_mask.to(dev).requires_grad_(True)
+        full, ms, ds, _, loss = mod_forward(pf, pm, [tf], pr.tmpl_mask.to(dev), sc, pr.targets.to(dev))
+        total = (full * w_mask.to(dev)).sum() + (ms * w_ms.to(dev)).sum() + (ds * w_ds.to(dev)).sum() + 2.0 * loss["cost_loss"]
+        total.backward()
+        return [t.grad.detach().cpu() for t in (pf, tf, sc, pm)]
+
+    want = run(lambda *a: orc.match_layer_forward(cfg, 0, *a), "cpu")
+    got = run(MatchModel(cfg, is_test=0), DEV)
+    for name, a, b in zip(("prop_feat", "tmpl_feat", "prop_score", "prop_mask"), got, want):
+        close(a, b, TOL * max(1.0, float(b.abs().max())), "grad " + name)
+
+
+def test_headline_shape_properties():
+    """N=50, K=10, 256x448 (BASELINE configs[1]) at full size: oracle comparison on one problem (expand=False keeps the
+    CPU time in seconds) plus size-independent properties on a batch."""
+    P, O, H, W = 50, 10, 256, 448
+    pr = make_problems(4, P, O, H, W, 512, seed=2000)
+    d = pr.to(DEV)
+    cfg = default_cfg(20, 5)
+    layer = MatchModel(cfg, is_test=1)
+    with torch.no_grad():
+        out = layer.forward_many(d.prop_feat, d.prop_mask, d.tmpl_feat, d.tmpl_mask, d.prop_score)
+        r = ops.mask_iou_pairwise(d.prop_mask, d.tmpl_mask, want_counts=True)
+    # IoU of a mask set with itself has a unit diagonal and is symmetric
+    self_iou = ops.mask_iou_pairwise(d.prop_mask[:, :16], d.prop_mask[:, :16])["iou"]
+    assert torch.equal(self_iou, self_iou.transpose(1, 2))
+    diag = torch.diagonal(self_iou, dim1=1, dim2=2)
+    areas = (d.prop_mask[:, :16].flatten(2) > 0.5).sum(2)
+    assert torch.equal(diag == 1, areas >= 32) or torch.all(diag[areas > 0] > 0.99)
+    # counts: inter <= min(area), a checksum of checksums against torch reductions
+    cnt = r["counts"]
+    inter = cnt[:, :O * P].view(4, O, P)
+    at, ap = cnt[:, O * P:O * P + O], cnt[:, O * P + O:]
+    assert torch.equal(ap, (d.prop_mask.flatten(2) > 0.5).sum(2).int())
+    assert torch.equal(at, (d.tmpl_mask.flatten(2) > 0.5).sum(2).int())
+    assert torch.all(inter <= torch.minimum(at[:, :, None], ap[:, None, :]))
+    # rows of the mean iterate stay close to the simplex; every template row picks exactly its arg-max proposal
+    assert torch.all(out["logic"].sum(2) >= 1)
+    b = 0
+    full, ms, ds, _, _ = orc.match_layer_forward(cfg, 1, pr.prop_feat[b], pr.prop_mask[b], [pr.tmpl_feat[b]],
+                                                  pr.tmpl_mask[b], pr.prop_score[b], None, expand=False)
+    close(out["full_outmask"][b], full, TOL, "full_outmask")
+    close(out["match_score"][b], ms, TOL, "match_score")
+    close(out["det_score"][b], ds, TOL, "det_score")
+    planted_hit = (out["Bmat"][:, :, :P].argmax(2).cpu() == pr.planted).float().mean().item()
+    assert planted_hit > 0.9                                     # the planted assignment is recovered
+
+
+def test_product_path_refuses_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        ops.mask_iou_pairwise(torch.zeros(1, 2, 8), torch.zeros(1, 1, 8))
+    with pytest.raises(AssertionError):
+        MatchModel(default_cfg(algo="bogus"), 1)
