@@ -1,0 +1,115 @@
+"""Batched drop-in for dmm/modules/dmm_model.py (the caller of the matching layer).
+
+Same class name, constructor and method signatures/returns as the reference ``DMM_Model``; what changes is HOW one
+frame of a batch of videos is matched: the reference loops over videos in Python with an ``.item()`` sync per video
+(dmm_model.py:117) and three 0/1-matrix ``torch.mm`` select/scatter passes (:133-135,:156); here all videos of the
+batch go through the kernels in one launch each, valid-template counts stay on the device (``n_tmpl``), and the
+scatter of the O valid rows into the F=maxseqlen output slots is the apply kernel's ``row_map``.
+"""
+import torch
+import torch.nn as nn
+
+from ..utils.checker import CHECK4D, CHECKEQ
+from .feature_extractor import make_roi_mask_feature_extractor
+from .match_model import MatchModel
+
+
+def _stack_pad(tensors, width, fill=0.0):
+    """list of [n_b, ...] -> [B, width, ...] (one copy; skipped when every n_b == width and inputs already form a batch)."""
+    if all(t.shape[0] == width for t in tensors):
+        return torch.stack(tensors, 0)
+    out = tensors[0].new_full((len(tensors), width) + tuple(tensors[0].shape[1:]), fill)
+    for b, t in enumerate(tensors):
+        out[b, :t.shape[0]] = t
+    return out
+
+
+class DMM_Model(nn.Module):
+    r""" container for all DMM modules: match_layer, feature_extractor (reference dmm_model.py:11-20) """
+
+    def __init__(self, cfgs, is_test=0):
+        super(DMM_Model, self).__init__()
+        self.match_layer = MatchModel(cfgs, is_test)
+        self.feature_extractor = make_roi_mask_feature_extractor()
+        self.match_algo = cfgs['matching']['algo']
+
+    # ------------------------------------------------------------------------------------------------------
+    def fill_template_dict(self, args, proposals, features, y_mask, tplt_valid_batch):
+        """First frame: pooled features of the ground-truth boxes become the templates (reference :22-46)."""
+        backbone_feature = features['backbone_feature']
+        refine_input_feat = features['refine_input_feat']
+        boxes_per_image = [len(box) for box in proposals]
+        result_alllevel = self.feature_extractor(backbone_feature, proposals)
+        feats = result_alllevel.split(boxes_per_image, dim=0)
+        tplt_dict = {}
+        for b, feat in enumerate(feats):
+            tplt_dict[b] = {'feat': [feat], 'refine_input_feat': [tuple([f[b] for f in refine_input_feat])]}
+        return tplt_dict
+
+    def prepare_tplt_feature(self, tplt_valid_vid, tplt_dict, bid):
+        """Valid template features of one video: rows :O of diag(valid) @ feat (reference :144-158); kept for API
+        compatibility -- the batched path does this for all videos at once in ``_gather``."""
+        O = int(tplt_valid_vid.sum().item())
+        OF_matrix = torch.diag(tplt_valid_vid).float()[:O, :]
+        tplt_feat = tplt_dict[bid]['feat']
+        assert (type(tplt_feat) == list)
+        self.tplt_feat_shape = tplt_feat[0].shape
+        return [OF_matrix @ t for t in tplt_feat], OF_matrix
+
+    # ------------------------------------------------------------------------------------------------------
+    def _gather(self, proposals, backbone_feature, tplt_dict, tplt_valid_batch, skip=None):
+        B = len(proposals)
+        boxes_per_image = [len(box) for box in proposals]
+        Pmax = max(max(boxes_per_image), 1)
+        pooled = self.feature_extractor(backbone_feature, proposals).split(boxes_per_image, dim=0)
+        prop_feat = _stack_pad(list(pooled), Pmax)
+        prop_mask = _stack_pad([p.get_field('mask').squeeze(1) for p in proposals], Pmax)
+        prop_score = _stack_pad([p.get_field('objectness') if 'objectness' in p.fields() else p.get_field('scores')
+                                 for p in proposals], Pmax)
+        dev = prop_mask.device
+        valid = tplt_valid_batch.to(dev).float().view(B, -1)                            # [B,F] 0/1
+        Fm = valid.shape[1]
+        n_tmpl = valid.sum(1).round().to(torch.int32)                                  # stays on the device
+        if skip is not None:
+            n_tmpl = torch.where(skip.to(dev), torch.zeros_like(n_tmpl), n_tmpl)
+        # reference semantics: rows :O of diag(valid) -> row i is valid[i]*e_i (dmm_model.py:152-154)
+        T = len(tplt_dict[0]['feat'])
+        tmpl_feat = torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)  # [B,T,F,D]
+        tmpl_feat = tmpl_feat * valid[:, None, :, None]
+        ar = torch.arange(Fm, device=dev, dtype=torch.int32)[None, :].expand(B, -1)
+        row_map = torch.where(valid > 0, ar, torch.full_like(ar, -1)).contiguous()      # scatter fused into K4
+        n_prop = torch.tensor(boxes_per_image, dtype=torch.int32, device=dev)
+        return prop_feat, prop_mask, prop_score, tmpl_feat, n_prop, n_tmpl, row_map, Fm
+
+    def _match(self, proposals, backbone_feature, mask_last_occurence, tplt_dict, tplt_valid_batch, targets, skip=None):
+        B, F, H, W = CHECK4D(mask_last_occurence)
+        CHECKEQ(len(proposals), B)
+        prop_feat, prop_mask, prop_score, tmpl_feat, n_prop, n_tmpl, row_map, Fm = self._gather(
+            proposals, backbone_feature, tplt_dict, tplt_valid_batch, skip)
+        CHECKEQ(Fm, F)
+        CHECKEQ(tuple(prop_mask.shape[-2:]), (H, W))
+        out = self.match_layer.forward_many(prop_feat, prop_mask, tmpl_feat, mask_last_occurence, prop_score, targets,
+                                            n_prop=n_prop, n_tmpl=n_tmpl, row_map=row_map, out_rows=F)
+        output_mask = out['full_outmask']                                              # [B,F,H,W], zero rows where invalid
+        empty = (n_tmpl == 0).view(B, 1, 1, 1)
+        # videos without templates keep their previous masks (reference :66-69,:118-122)
+        out_mask_last = torch.where(empty, mask_last_occurence.to(output_mask.dtype), output_mask)
+        return output_mask, out_mask_last, out, n_tmpl
+
+    def inference(self, infos, proposals, backbone_feature, mask_last_occurence, tplt_dict, target=None):
+        """reference :48-86 -> (output_mask [B,F,H,W], tplt_dict, match_loss [], out_mask_last [B,F,H,W])"""
+        extra = infos['extra_frame']
+        skip = torch.as_tensor(extra).bool().view(-1) if extra is not None else None
+        output_mask, out_mask_last, _, _ = self._match(proposals, backbone_feature, mask_last_occurence, tplt_dict,
+                                                       infos['valid'], None if target is None else torch.stack(list(target), 0)
+                                                       if not torch.is_tensor(target) else target, skip)
+        return output_mask, tplt_dict, [], out_mask_last
+
+    def forward(self, args, proposals, backbone_feature, mask_last_occurence, tplt_dict, tplt_valid_batch, targets):
+        """reference :88-142 -> (output_mask [B,F,H,W], tplt_dict, match_loss list (one scalar per video), out_mask_last)"""
+        assert (targets is not None)
+        output_mask, out_mask_last, out, n_tmpl = self._match(proposals, backbone_feature, mask_last_occurence, tplt_dict,
+                                                              tplt_valid_batch, targets)
+        loss = out['cost_loss'] * (n_tmpl > 0).float()       # videos without templates contribute prop_feat.sum()*0
+        match_loss = list(loss.unbind(0))
+        return output_mask, tplt_dict, match_loss, out_mask_last

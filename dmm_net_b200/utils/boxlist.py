@@ -1,0 +1,34 @@
+"""Minimal stand-in for maskrcnn_benchmark.structures.bounding_box.BoxList (un-vendored dependency of the
+reference): just what the matching path touches -- ``bbox`` [n,4] xyxy, ``get_field/add_field/fields`` and ``len``
+(dmm/modules/dmm_model.py:59-71,106-123; dmm/modules/feature_extractor.py:32-37)."""
+import torch
+
+
+class BoxList(object):
+    def __init__(self, bbox, image_size=None, mode="xyxy"):
+        bbox = torch.as_tensor(bbox, dtype=torch.float32)
+        assert bbox.dim() == 2 and bbox.shape[-1] == 4, bbox.shape
+        assert mode == "xyxy"
+        self.bbox, self.size, self.mode = bbox, image_size, mode
+        self.extra_fields = {}
+
+    def add_field(self, name, data):
+        self.extra_fields[name] = data
+
+    def get_field(self, name):
+        return self.extra_fields[name]
+
+    def has_field(self, name):
+        return name in self.extra_fields
+
+    def fields(self):
+        return list(self.extra_fields.keys())
+
+    def to(self, device):
+        out = BoxList(self.bbox.to(device), self.size, self.mode)
+        for k, v in self.extra_fields.items():
+            out.add_field(k, v.to(device) if hasattr(v, "to") else v)
+        return out
+
+    def __len__(self):
+        return self.bbox.shape[0]

@@ -56,6 +56,11 @@ def layer_case(name, P, O, H, W, D, max_iter, proj_iter, is_test, config, index,
                                                  {"proposed": pr.prop_mask, "template": pr.tmpl_mask},
                                                  {"proposal_score": sc}, pr.targets)
         _, _, _, logic, bmat = layer.match_with_first_frame(sim, P, O, pr.prop_mask.float(), sc, pr.tmpl_mask)
+        sim_pad = sim.detach()
+        if P <= O:
+            sim_pad = torch.cat([sim_pad, sim_pad.new_zeros(O, O + 1 - P)], 1)
+        _, _, X_list_ref, _ = relax_matching(-sim_pad, max_iter=max_iter, proj_iter=proj_iter, lr=lr)
+        out["n_list"] = np.int64(len(X_list_ref))          # len(X_list): where the reference's outer exit fired
         full, ms, ds, full2, loss = layer(pf, pr.prop_mask, [tf], pr.tmpl_mask, sc, pr.targets)
         assert full is full2
         if not is_test:

@@ -1,0 +1,114 @@
+"""GPU parity of the rows either side of the layer: K5 proposal-feature pooling (vs torchvision's legacy ROIAlign,
+the stand-in oracle -- parity unpinned by the reference) and the batched DMM_Model container (vs the per-video loop
+of the oracle's dmm_container_forward, reference dmm_model.py:88-158)."""
+import numpy as np
+import pytest
+import torch
+
+from dmm_net_b200 import ops
+from dmm_net_b200.modules.dmm_model import DMM_Model
+from dmm_net_b200.modules.feature_extractor import make_roi_mask_feature_extractor
+from dmm_net_b200.synth import default_cfg, make_problems
+from dmm_net_b200.utils.boxlist import BoxList
+from oracle import match_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _feats(gen, N, C, H, W):
+    return [torch.randn(N, C, H // s, W // s, generator=gen) for s in (4, 8, 16, 32)]
+
+
+def _boxes(gen, n, H, W):
+    x1 = torch.rand(n, generator=gen) * (W - 8)
+    y1 = torch.rand(n, generator=gen) * (H - 8)
+    w = 4 + torch.rand(n, generator=gen) * (W / 2)
+    h = 4 + torch.rand(n, generator=gen) * (H / 2)
+    return torch.stack([x1, y1, (x1 + w).clamp(max=W - 1), (y1 + h).clamp(max=H - 1)], 1)
+
+
+def test_roi_mean_pool_forward_and_backward():
+    gen = torch.Generator().manual_seed(4)
+    N, C, H, W = 2, 24, 256, 448
+    feats = _feats(gen, N, C, H, W)
+    rois = torch.cat([torch.cat([torch.full((9, 1), float(i)), _boxes(gen, 9, H, W)], 1) for i in range(N)], 0)
+    rois = torch.cat([rois, torch.tensor([[0, -30.0, -10.0, 20.0, 40.0], [1, 440.0, 250.0, 470.0, 280.0],
+                                          [1, 100.0, 100.0, 100.0, 100.0], [0, 0.0, 0.0, 447.0, 255.0]])], 0)
+    want_in = [f.clone().requires_grad_(True) for f in feats]
+    want = orc.roi_mean_pool(want_in, rois)
+    got_in = [f.to(DEV).requires_grad_(True) for f in feats]
+    got = ops.roi_mean_pool(got_in, rois.to(DEV))
+    assert got.shape == (rois.shape[0], 4 * C)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=0, atol=1e-5)
+    w = torch.randn(want.shape, generator=gen)
+    (want * w).sum().backward()
+    (got * w.to(DEV)).sum().backward()
+    for a, b in zip(got_in, want_in):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=0, atol=1e-5)
+
+
+def test_feature_extractor_module_layout():
+    gen = torch.Generator().manual_seed(8)
+    feats = [f.to(DEV) for f in _feats(gen, 2, 128, 128, 192)]
+    props = [BoxList(_boxes(gen, 5, 128, 192)).to(DEV), BoxList(_boxes(gen, 3, 128, 192)).to(DEV)]
+    fe = make_roi_mask_feature_extractor()
+    out = fe(tuple(feats), props)
+    assert out.shape == (8, 512)
+    rois = fe.convert_to_roi_format(props)
+    assert rois.shape == (8, 5) and rois[:5, 0].eq(0).all() and rois[5:, 0].eq(1).all()
+    want = orc.roi_mean_pool([f.cpu() for f in feats], rois.cpu())
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("is_test", [1, 0])
+def test_batched_container_equals_per_video_loop(is_test):
+    B, P, Fm, H, W, C = 4, 12, 5, 64, 96, 16
+    gen = torch.Generator().manual_seed(21)
+    pr = make_problems(B, P, Fm, H, W, 4 * C, seed=31, with_targets=True)
+    feats = _feats(gen, B, C, H, W)
+    n_prop = [12, 7, 12, 3]
+    valid = torch.tensor([[1, 1, 1, 0, 0], [1, 0, 0, 0, 0], [0, 0, 0, 0, 0], [1, 1, 1, 1, 1]], dtype=torch.float32)
+    boxes = [_boxes(gen, n, H, W) for n in n_prop]
+    tboxes = [_boxes(gen, Fm, H, W) for _ in range(B)]
+    cfg = default_cfg(10, 5)
+
+    def boxlists(dev):
+        out = []
+        for b in range(B):
+            bl = BoxList(boxes[b])
+            bl.add_field('mask', pr.prop_mask[b, :n_prop[b]].unsqueeze(1))
+            bl.add_field('scores', pr.prop_score[b, :n_prop[b]])
+            out.append(bl.to(dev))
+        return out
+
+    # ---- oracle: pooled features via torchvision ROIAlign, then the per-video loop ------------------------
+    rois = torch.cat([torch.cat([torch.full((n_prop[b], 1), float(b)), boxes[b]], 1) for b in range(B)], 0)
+    pooled = orc.roi_mean_pool(feats, rois).split(n_prop, 0)
+    trois = torch.cat([torch.cat([torch.full((Fm, 1), float(b)), tboxes[b]], 1) for b in range(B)], 0)
+    tfeat = orc.roi_mean_pool(feats, trois).split([Fm] * B, 0)
+    want_out, want_loss, want_last = orc.dmm_container_forward(
+        cfg, is_test, list(pooled), [pr.prop_mask[b, :n_prop[b]] for b in range(B)],
+        [pr.prop_score[b, :n_prop[b]] for b in range(B)], list(tfeat), pr.tmpl_mask, valid,
+        None if is_test else pr.targets)
+
+    # ---- product: batched container ----------------------------------------------------------------------
+    model = DMM_Model(cfg, is_test=is_test).to(DEV)
+    dfeats = tuple(f.to(DEV) for f in feats)
+    tplt = model.fill_template_dict(None, [BoxList(tboxes[b]).to(DEV) for b in range(B)],
+                                    {'backbone_feature': dfeats, 'refine_input_feat': dfeats}, None, valid)
+    if is_test:
+        with torch.no_grad():
+            out, _, loss, last = model.inference({'args': None, 'shape': (H, W), 'extra_frame': [0] * B, 'valid': valid.to(DEV)},
+                                                 boxlists(DEV), dfeats, pr.tmpl_mask.to(DEV), tplt)
+        assert loss == []
+    else:
+        out, _, loss, last = model(None, boxlists(DEV), dfeats, pr.tmpl_mask.to(DEV), tplt, valid.to(DEV), pr.targets.to(DEV))
+        assert len(loss) == B
+        k = 0
+        for b in range(B):
+            if valid[b].sum() == 0:
+                assert float(loss[b]) == 0.0
+            np.testing.assert_allclose(float(loss[b]), float(want_loss[b]), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want_out.numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(last.detach().cpu().numpy(), want_last.numpy(), rtol=0, atol=1e-4)
