@@ -38,24 +38,28 @@ struct IouParams {
   int cnt;                         // Otot*P + Otot + P
 };
 
+// Unconditional 4-pixel read: indices are clamped into the row so the load never branches (a predicated-off or
+// branched load would break the back-to-back LDG issue and serialise the 16 loads of a chunk on one scoreboard:
+// measured 26 % -> see profiles/); validity is folded into the ballot predicate instead.
 template <bool VEC>
 __device__ __forceinline__ float4 load_px4(const float* row, int px, int HW) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row == nullptr) return v;
+  float4 v;
   if (VEC) {
-    if (px < HW) v = ld_stream_f4(row + px);
+    v = ld_stream_f4(row + min(px, HW - 4));
   } else {
-    if (px + 0 < HW) v.x = ld_stream_f1(row + px + 0);
-    if (px + 1 < HW) v.y = ld_stream_f1(row + px + 1);
-    if (px + 2 < HW) v.z = ld_stream_f1(row + px + 2);
-    if (px + 3 < HW) v.w = ld_stream_f1(row + px + 3);
+    const int last = HW - 1;
+    v.x = ld_stream_f1(row + min(px + 0, last));
+    v.y = ld_stream_f1(row + min(px + 1, last));
+    v.z = ld_stream_f1(row + min(px + 2, last));
+    v.w = ld_stream_f1(row + min(px + 3, last));
   }
   return v;
 }
 
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const IouParams p) {
-  __shared__ const float* row_ptr[kMaxRows];
+  __shared__ const float* row_ptr[kMaxRows];   // never null: padding rows alias a real row and are masked by row_ok
+  __shared__ uint32_t row_ok[kMaxRows];
   __shared__ uint32_t bits[2][kWords][kRowPad];
   __shared__ int red[kTileO * kMaxRows + kMaxRows];
 
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
   const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
   const int p0 = ptile * p.PT, o0 = otile * p.OT;
   const int pcnt = min(p.PT, p.P - p0), ocnt = min(p.OT, p.Otot - o0);
-  const int rows = pcnt + ocnt, units = rows * 2;
+  const int rows = pcnt + ocnt;
 
   if (tid < kMaxRows) {
     const float* ptr = nullptr;
@@ -80,9 +84,9 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
         ptr = p.tmpl2 + (long long)b * p.tmpl2_bs + (long long)(t - p.O) * p.HW;
       }
     }
-    row_ptr[tid] = ptr;
+    row_ok[tid] = ptr != nullptr;
+    row_ptr[tid] = ptr ? ptr : p.prop + (long long)b * p.prop_bs;  // any readable row of this problem
   }
-  for (int i = tid; i < 2 * kWords * kRowPad; i += kThreads) (&bits[0][0][0])[i] = 0u;
   for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kThreads) red[i] = 0;
   __syncthreads();
 
@@ -94,39 +98,50 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
   for (int o = 0; o < kTileO; ++o) acc[o][0] = acc[o][1] = 0;
   int area0 = 0, area1 = 0;  // popcount of row `lane` and row `lane+32` (covers proposals AND templates)
 
+  // this warp's 16 row pieces per chunk: unit u = warp + 8k -> (row u>>1, 128-pixel group u&1); 8*16 = all 64 rows
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxUnits; ++k) okmask |= row_ok[(warp + kWarps * k) >> 1] << k;
+  const int lane_px = lane * 4;
+
   float4 v[kMaxUnits];
   auto issue = [&](int chunk) {
+    const int base = chunk * kChunkPx;
 #pragma unroll
     for (int k = 0; k < kMaxUnits; ++k) {
       const int u = warp + kWarps * k;
-      if (u < units) {
-        const int px = chunk * kChunkPx + (u & 1) * 128 + lane * 4;
-        v[k] = load_px4<VEC>(row_ptr[u >> 1], px, p.HW);
-      }
+      v[k] = load_px4<VEC>(row_ptr[u >> 1], base + (u & 1) * 128 + lane_px, p.HW);
     }
   };
 
   if (c0 < c1) issue(c0);
   for (int c = c0; c < c1; ++c) {
     const int buf = (c - c0) & 1;
-    // ---- phase A: threshold + ballot -> bit planes ------------------------------------------------------
+    const int base = c * kChunkPx;
+    // ---- phase A: threshold + ballot -> bit planes (straight-line: all 16 units, padding masked) ---------
 #pragma unroll
     for (int k = 0; k < kMaxUnits; ++k) {
       const int u = warp + kWarps * k;
-      if (u < units) {
-        const uint32_t w0 = __ballot_sync(0xffffffffu, v[k].x > 0.5f);
-        const uint32_t w1 = __ballot_sync(0xffffffffu, v[k].y > 0.5f);
-        const uint32_t w2 = __ballot_sync(0xffffffffu, v[k].z > 0.5f);
-        const uint32_t w3 = __ballot_sync(0xffffffffu, v[k].w > 0.5f);
-        // bit i of word j is pixel 4*i+j of the 128-pixel group: a fixed permutation shared by all rows,
-        // and AND/popcount do not care about bit order.
-        if (lane < 4) {
-          const uint32_t w = lane == 0 ? w0 : (lane == 1 ? w1 : (lane == 2 ? w2 : w3));
-          bits[buf][(u & 1) * 4 + lane][u >> 1] = w;
-        }
+      const int px = base + (u & 1) * 128 + lane_px;
+      const bool ok = (okmask >> k) & 1u;
+      bool in0, in1, in2, in3;
+      if (VEC) {
+        in0 = in1 = in2 = in3 = ok && px < p.HW;
+      } else {
+        in0 = ok && px + 0 < p.HW; in1 = ok && px + 1 < p.HW; in2 = ok && px + 2 < p.HW; in3 = ok && px + 3 < p.HW;
+      }
+      const uint32_t w0 = __ballot_sync(0xffffffffu, in0 && v[k].x > 0.5f);
+      const uint32_t w1 = __ballot_sync(0xffffffffu, in1 && v[k].y > 0.5f);
+      const uint32_t w2 = __ballot_sync(0xffffffffu, in2 && v[k].z > 0.5f);
+      const uint32_t w3 = __ballot_sync(0xffffffffu, in3 && v[k].w > 0.5f);
+      // bit i of word j is pixel 4*i+j of the 128-pixel group: a fixed permutation shared by all rows,
+      // and AND/popcount do not care about bit order.
+      if (lane < 4) {
+        const uint32_t w = lane == 0 ? w0 : (lane == 1 ? w1 : (lane == 2 ? w2 : w3));
+        bits[buf][(u & 1) * 4 + lane][u >> 1] = w;
       }
     }
-    if (c + 1 < c1) issue(c + 1);  // next chunk's loads fly during the barrier and phase B
+    if (c + 1 < c1) issue(c + 1);  // next chunk's 16 loads per lane fly during the barrier and phase B
     __syncthreads();
     // ---- phase B: warp w owns word w; lanes are proposals (lane, lane+32) --------------------------------
     {

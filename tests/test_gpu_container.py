@@ -45,7 +45,7 @@ def test_roi_mean_pool_forward_and_backward():
     (want * w).sum().backward()
     (got * w.to(DEV)).sum().backward()
     for a, b in zip(got_in, want_in):
-        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=0, atol=1e-5)
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-4, atol=1e-5)   # fp32 atomics order
 
 
 def test_feature_extractor_module_layout():

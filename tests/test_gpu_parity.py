@@ -251,10 +251,8 @@ def test_gradients_match_oracle_autograd():
     w_mask, w_ms, w_ds = torch.rand(O, H, W, generator=gen), torch.rand(O, generator=gen), torch.rand(O, generator=gen)
 
     def run(mod_forward, dev):
-        pf = pr.prop_feat.to(dev).requires_grad_(True)
-        tf = pr.tmpl_feat.to(dev).requires_grad_(True)
-        sc = pr.prop_score.to(dev).requires_grad_(True)
-        pm = pr.prop_mask.to(dev).requires_grad_(True)
+        leaf = lambda t: t.detach().clone().to(dev).requires_grad_(True)
+        pf, tf, sc, pm = leaf(pr.prop_feat), leaf(pr.tmpl_feat), leaf(pr.prop_score), leaf(pr.prop_mask)
         full, ms, ds, _, loss = mod_forward(pf, pm, [tf], pr.tmpl_mask.to(dev), sc, pr.targets.to(dev))
         total = (full * w_mask.to(dev)).sum() + (ms * w_ms.to(dev)).sum() + (ds * w_ds.to(dev)).sum() + 2.0 * loss["cost_loss"]
         total.backward()
