@@ -21,7 +21,6 @@ constexpr int kWords = kChunkPx / 32;         // 8 bit-plane words per row per c
 constexpr int kMaxRows = 64;                  // masks per tile (proposals + templates)
 constexpr int kMaxUnits = kMaxRows * 2 / kWarps;  // 512-byte row pieces per warp per chunk (16)
 constexpr int kTileO = 16;                    // templates per tile (register counters)
-constexpr int kRowPad = kMaxRows + 1;
 static_assert(kWords == kWarps, "one bit-plane word per warp in phase B");
 
 struct IouParams {
@@ -38,9 +37,10 @@ struct IouParams {
   int cnt;                         // Otot*P + Otot + P
 };
 
-// Unconditional 4-pixel read: indices are clamped into the row so the load never branches (a predicated-off or
-// branched load would break the back-to-back LDG issue and serialise the 16 loads of a chunk on one scoreboard:
-// measured 26 % -> see profiles/); validity is folded into the ballot predicate instead.
+// Unconditional 4-pixel read: the index is clamped into the row so the load never branches.  (Round-1 profile: with
+// branched loads ptxas put every LDG behind a scoreboard wait of the previous one -- 16 serialised loads per chunk,
+// 26 % of the HBM roofline; back-to-back loads gave 56-70 %.)  Pixels past the end only exist in a row's last
+// chunk, which takes the masked path below.
 template <bool VEC>
 __device__ __forceinline__ float4 load_px4(const float* row, int px, int HW) {
   float4 v;
@@ -56,11 +56,12 @@ __device__ __forceinline__ float4 load_px4(const float* row, int px, int HW) {
   return v;
 }
 
-template <bool VEC>
+template <bool VEC, int TO>   // TO: template-row counters per lane (ocnt <= TO <= kTileO), loops run unpredicated
 __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const IouParams p) {
-  __shared__ const float* row_ptr[kMaxRows];   // never null: padding rows alias a real row and are masked by row_ok
-  __shared__ uint32_t row_ok[kMaxRows];
-  __shared__ uint32_t bits[2][kWords][kRowPad];
+  // Padding rows (beyond this problem's P+O, or beyond n_prop/n_tmpl) alias a real row: their bits are garbage but
+  // the finalize kernel never reads the counters of padding rows, so the hot loop carries no per-row predicate.
+  __shared__ const float* row_ptr[kMaxRows];
+  __shared__ uint32_t bits[2][2][kMaxRows + kTileO][4];   // [buffer][128-px group][row][word]: one STS.128 per row piece
   __shared__ int red[kTileO * kMaxRows + kMaxRows];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -84,7 +85,6 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
         ptr = p.tmpl2 + (long long)b * p.tmpl2_bs + (long long)(t - p.O) * p.HW;
       }
     }
-    row_ok[tid] = ptr != nullptr;
     row_ptr[tid] = ptr ? ptr : p.prop + (long long)b * p.prop_bs;  // any readable row of this problem
   }
   for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kThreads) red[i] = 0;
@@ -92,79 +92,81 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
 
   const int c0 = s * p.chunks_per_slab;
   const int c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
+  const int tail_chunk = (p.HW % kChunkPx) ? p.n_chunks - 1 : -1;   // the only chunk with pixels past the row end
 
-  int acc[kTileO][2];
+  int acc[TO][2];
 #pragma unroll
-  for (int o = 0; o < kTileO; ++o) acc[o][0] = acc[o][1] = 0;
+  for (int o = 0; o < TO; ++o) acc[o][0] = acc[o][1] = 0;
   int area0 = 0, area1 = 0;  // popcount of row `lane` and row `lane+32` (covers proposals AND templates)
 
   // this warp's 16 row pieces per chunk: unit u = warp + 8k -> (row u>>1, 128-pixel group u&1); 8*16 = all 64 rows
-  uint32_t okmask = 0;
-#pragma unroll
-  for (int k = 0; k < kMaxUnits; ++k) okmask |= row_ok[(warp + kWarps * k) >> 1] << k;
   const int lane_px = lane * 4;
-
+  const int grp_b = warp >> 2, word_b = warp & 3;   // phase B: this warp's bit-plane word of the chunk
   float4 v[kMaxUnits];
-  auto issue = [&](int chunk) {
-    const int base = chunk * kChunkPx;
-#pragma unroll
-    for (int k = 0; k < kMaxUnits; ++k) {
-      const int u = warp + kWarps * k;
-      v[k] = load_px4<VEC>(row_ptr[u >> 1], base + (u & 1) * 128 + lane_px, p.HW);
-    }
-  };
 
-  if (c0 < c1) issue(c0);
+#define DMM_ISSUE(chunk)                                                                        \
+  {                                                                                             \
+    const int base_ = (chunk) * kChunkPx + lane_px;                                             \
+    _Pragma("unroll") for (int k = 0; k < kMaxUnits; ++k) {                                     \
+      const int u = warp + kWarps * k;                                                          \
+      v[k] = load_px4<VEC>(row_ptr[u >> 1], base_ + (u & 1) * 128, p.HW);                       \
+    }                                                                                           \
+  }
+
+  if (c0 < c1) DMM_ISSUE(c0);
   for (int c = c0; c < c1; ++c) {
     const int buf = (c - c0) & 1;
-    const int base = c * kChunkPx;
-    // ---- phase A: threshold + ballot -> bit planes (straight-line: all 16 units, padding masked) ---------
+    // ---- phase A: threshold + ballot -> bit planes --------------------------------------------------------
+    // bit i of word j is pixel 4*i+j of the 128-pixel group: a fixed permutation shared by all rows, and
+    // AND/popcount do not care about bit order.
+    if (c != tail_chunk) {
 #pragma unroll
-    for (int k = 0; k < kMaxUnits; ++k) {
-      const int u = warp + kWarps * k;
-      const int px = base + (u & 1) * 128 + lane_px;
-      const bool ok = (okmask >> k) & 1u;
-      bool in0, in1, in2, in3;
-      if (VEC) {
-        in0 = in1 = in2 = in3 = ok && px < p.HW;
-      } else {
-        in0 = ok && px + 0 < p.HW; in1 = ok && px + 1 < p.HW; in2 = ok && px + 2 < p.HW; in3 = ok && px + 3 < p.HW;
+      for (int k = 0; k < kMaxUnits; ++k) {
+        const int u = warp + kWarps * k;
+        uint4 w;
+        w.x = __ballot_sync(0xffffffffu, v[k].x > 0.5f);
+        w.y = __ballot_sync(0xffffffffu, v[k].y > 0.5f);
+        w.z = __ballot_sync(0xffffffffu, v[k].z > 0.5f);
+        w.w = __ballot_sync(0xffffffffu, v[k].w > 0.5f);
+        // every lane holds the same four words: an unconditional same-address STS.128 is one wavefront, no branch
+        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
       }
-      const uint32_t w0 = __ballot_sync(0xffffffffu, in0 && v[k].x > 0.5f);
-      const uint32_t w1 = __ballot_sync(0xffffffffu, in1 && v[k].y > 0.5f);
-      const uint32_t w2 = __ballot_sync(0xffffffffu, in2 && v[k].z > 0.5f);
-      const uint32_t w3 = __ballot_sync(0xffffffffu, in3 && v[k].w > 0.5f);
-      // bit i of word j is pixel 4*i+j of the 128-pixel group: a fixed permutation shared by all rows,
-      // and AND/popcount do not care about bit order.
-      if (lane < 4) {
-        const uint32_t w = lane == 0 ? w0 : (lane == 1 ? w1 : (lane == 2 ? w2 : w3));
-        bits[buf][(u & 1) * 4 + lane][u >> 1] = w;
+    } else {
+      const int base = c * kChunkPx + lane_px;
+#pragma unroll
+      for (int k = 0; k < kMaxUnits; ++k) {
+        const int u = warp + kWarps * k;
+        const int px = base + (u & 1) * 128;
+        uint4 w;
+        w.x = __ballot_sync(0xffffffffu, px + 0 < p.HW && v[k].x > 0.5f);
+        w.y = __ballot_sync(0xffffffffu, px + 1 < p.HW && v[k].y > 0.5f);
+        w.z = __ballot_sync(0xffffffffu, px + 2 < p.HW && v[k].z > 0.5f);
+        w.w = __ballot_sync(0xffffffffu, px + 3 < p.HW && v[k].w > 0.5f);
+        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
       }
     }
-    if (c + 1 < c1) issue(c + 1);  // next chunk's 16 loads per lane fly during the barrier and phase B
+    if (c + 1 < c1) DMM_ISSUE(c + 1);  // next chunk's 16 loads per lane fly during the barrier and phase B
     __syncthreads();
-    // ---- phase B: warp w owns word w; lanes are proposals (lane, lane+32) --------------------------------
+    // ---- phase B: warp w owns word w of the chunk; lanes are proposals (lane, lane+32) ---------------------
     {
-      const uint32_t* wrow = bits[buf][warp];
-      const uint32_t b0 = wrow[lane], b1 = wrow[lane + 32];
+      const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
       area0 += __popc(b0);
       area1 += __popc(b1);
 #pragma unroll
-      for (int o = 0; o < kTileO; ++o) {
-        if (o < ocnt) {
-          const uint32_t a = wrow[pcnt + o];
-          acc[o][0] += __popc(a & b0);
-          acc[o][1] += __popc(a & b1);
-        }
+      for (int o = 0; o < TO; ++o) {   // rows past ocnt hold stale bits: counted, never written out
+        const uint32_t a = bits[buf][grp_b][pcnt + o][word_b];   // smem broadcast
+        acc[o][0] += __popc(a & b0);
+        acc[o][1] += __popc(a & b1);
       }
     }
     // the double-buffered bit planes make a second barrier unnecessary: buffer `buf` is rewritten in
     // iteration c+2, which every warp enters only after the barrier of iteration c+1.
   }
+#undef DMM_ISSUE
 
   // ---- cross-warp reduction of this slab ---------------------------------------------------------------
 #pragma unroll
-  for (int o = 0; o < kTileO; ++o) {
+  for (int o = 0; o < TO; ++o) {
     if (o < ocnt) {
       atomicAdd(&red[o * kMaxRows + lane], acc[o][0]);
       atomicAdd(&red[o * kMaxRows + lane + 32], acc[o][1]);
@@ -306,10 +308,16 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
   const bool vec = (HW % 4 == 0) && aligned16(prop) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
                    (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
   dim3 grid(pl.S, B, pl.n_ptiles * pl.n_otiles);
-  if (vec)
-    mask_iou_partial_kernel<true><<<grid, kThreads, 0, st>>>(kp);
-  else
-    mask_iou_partial_kernel<false><<<grid, kThreads, 0, st>>>(kp);
+#define DMM_LAUNCH(V, T) mask_iou_partial_kernel<V, T><<<grid, kThreads, 0, st>>>(kp)
+  const int to = pl.OT <= 4 ? 4 : (pl.OT <= 8 ? 8 : (pl.OT <= 12 ? 12 : 16));
+  if (vec) {
+    if (to == 4) DMM_LAUNCH(true, 4); else if (to == 8) DMM_LAUNCH(true, 8);
+    else if (to == 12) DMM_LAUNCH(true, 12); else DMM_LAUNCH(true, 16);
+  } else {
+    if (to == 4) DMM_LAUNCH(false, 4); else if (to == 8) DMM_LAUNCH(false, 8);
+    else if (to == 12) DMM_LAUNCH(false, 12); else DMM_LAUNCH(false, 16);
+  }
+#undef DMM_LAUNCH
   int rc = check_launch();
   if (rc) return rc;
 
