@@ -9,6 +9,8 @@
 //     broadcasts: popc(a & b) into O x 2 register counters per lane;
 //   - per-slab int32 partials go to a workspace (no atomics, no memset), a second tiny kernel adds the
 //     slabs and forms  inter / (float(|A|+|B|-inter) + 1e-6f)  -- integer-exact, so bit-equal to the reference.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dmm {
@@ -189,6 +191,208 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
     for (int i = tid; i < pcnt; i += kThreads) area_p[p0 + i] = red[kTileO * kMaxRows + i];
 }
 
+// =========================================================================================================
+// K1, TMA variant: the same computation with the row pieces staged by the TMA engine.
+//   - rows are contiguous 1-D runs, so the copy is cp.async.bulk (SASS UBLKCP) global -> shared, one per row piece,
+//     completing on an mbarrier with expect_tx: a kStages-deep ring of [64 rows][256 px] fp32 stages (64 KB each);
+//   - no register staging: 16 consumer warps read the landed stage with conflict-free LDS.128, ballot, popcount;
+//   - stage reuse needs no "empty" barrier: a stage is refilled right after the __syncthreads() that follows the
+//     last read of it (the reads have retired: their values fed the ballots).
+// Requires 16-byte aligned rows (HW % 4 == 0), like the vector path; the LDG kernel covers everything else.
+// =========================================================================================================
+constexpr int kTmaThreads = 512;
+constexpr int kTmaWarps = kTmaThreads / 32;
+constexpr int kStages = 3;
+constexpr int kStageFloats = kMaxRows * kChunkPx;                 // 64 KB per stage
+constexpr size_t kTmaDynSmem = (size_t)kStages * kStageFloats * sizeof(float);
+constexpr int kTmaUnits = kMaxRows * 2 / kTmaWarps;               // 8 row pieces per warp per chunk
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+template <int TO>
+__global__ void __launch_bounds__(kTmaThreads, 1) mask_iou_partial_tma_kernel(const IouParams p) {
+  constexpr int TH = TO / 2;                                      // template counters per warp half
+  extern __shared__ __align__(128) float stage[];                 // [kStages][kMaxRows][kChunkPx]
+  __shared__ const float* row_ptr[kMaxRows];
+  __shared__ uint32_t row_ok[kMaxRows];
+  __shared__ uint32_t bits[2][2][kMaxRows + kTileO][4];
+  __shared__ int red[kTileO * kMaxRows + kMaxRows];
+  __shared__ __align__(8) unsigned long long full_bar[kStages];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int ptile = blockIdx.z % p.n_ptiles, otile = blockIdx.z / p.n_ptiles;
+  const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
+  const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
+  const int p0 = ptile * p.PT, o0 = otile * p.OT;
+  const int pcnt = min(p.PT, p.P - p0), ocnt = min(p.OT, p.Otot - o0);
+  const int rows = pcnt + ocnt;
+
+  if (tid < kMaxRows) {
+    const float* ptr = nullptr;
+    if (tid < pcnt) {
+      if (p0 + tid < np) ptr = p.prop + (long long)b * p.prop_bs + (long long)(p0 + tid) * p.HW;
+    } else if (tid < rows) {
+      const int t = o0 + tid - pcnt;
+      if (t < p.O) {
+        if (t < nt) ptr = p.tmpl + (long long)b * p.tmpl_bs + (long long)t * p.HW;
+      } else if (t - p.O < nt) {
+        ptr = p.tmpl2 + (long long)b * p.tmpl2_bs + (long long)(t - p.O) * p.HW;
+      }
+    }
+    row_ptr[tid] = ptr;
+    row_ok[tid] = ptr != nullptr;
+  }
+  for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kTmaThreads) red[i] = 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(&full_bar[st]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int c0 = s * p.chunks_per_slab;
+  const int c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
+  const int nchunks = max(c1 - c0, 0);
+  const int tail_chunk = (p.HW % kChunkPx) ? p.n_chunks - 1 : -1;
+
+  // producer = warp 0: lane 0 arms the barrier with the stage's byte count, then every lane copies its rows
+  const uint32_t ok0 = row_ok[lane], ok1 = row_ok[lane + 32];
+  const int nvalid = __popc(__ballot_sync(0xffffffffu, ok0)) + __popc(__ballot_sync(0xffffffffu, ok1));
+  auto produce = [&](int i) {
+    const int st = i % kStages;
+    const int px0 = (c0 + i) * kChunkPx;
+    const uint32_t bytes = (uint32_t)min(kChunkPx, p.HW - px0) * 4u;
+    const uint32_t bar = smem_u32(&full_bar[st]);
+    if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)nvalid);
+    __syncwarp();
+    float* dst = stage + (size_t)st * kStageFloats;
+    if (ok0) bulk_g2s(smem_u32(dst + lane * kChunkPx), row_ptr[lane] + px0, bytes, bar);
+    if (ok1) bulk_g2s(smem_u32(dst + (lane + 32) * kChunkPx), row_ptr[lane + 32] + px0, bytes, bar);
+  };
+  if (warp == 0) {
+    for (int i = 0; i < kStages && i < nchunks; ++i) produce(i);
+  }
+
+  int acc[TH][2];
+#pragma unroll
+  for (int o = 0; o < TH; ++o) acc[o][0] = acc[o][1] = 0;
+  int area0 = 0, area1 = 0;
+  const int word = warp & 7, half = warp >> 3;
+  const int grp_b = word >> 2, word_b = word & 3;
+  const int lane_px = lane * 4;
+
+  for (int i = 0; i < nchunks; ++i) {
+    const int c = c0 + i, st = i % kStages, buf = i & 1;
+    mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((i / kStages) & 1));
+    const float* sbase = stage + (size_t)st * kStageFloats;
+    // ---- phase A: landed stage -> bit planes (8 row pieces per warp) --------------------------------------
+    if (c != tail_chunk) {
+#pragma unroll
+      for (int k = 0; k < kTmaUnits; ++k) {
+        const int u = warp + kTmaWarps * k;
+        const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
+        uint4 w;
+        w.x = __ballot_sync(0xffffffffu, v.x > 0.5f);
+        w.y = __ballot_sync(0xffffffffu, v.y > 0.5f);
+        w.z = __ballot_sync(0xffffffffu, v.z > 0.5f);
+        w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
+        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
+      }
+    } else {
+      const int base = c * kChunkPx + lane_px;
+#pragma unroll
+      for (int k = 0; k < kTmaUnits; ++k) {
+        const int u = warp + kTmaWarps * k;
+        const int px = base + (u & 1) * 128;
+        const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
+        uint4 w;   // bytes past the row end were not copied: stale smem, masked here (HW % 4 == 0: all four together)
+        w.x = __ballot_sync(0xffffffffu, px < p.HW && v.x > 0.5f);
+        w.y = __ballot_sync(0xffffffffu, px < p.HW && v.y > 0.5f);
+        w.z = __ballot_sync(0xffffffffu, px < p.HW && v.z > 0.5f);
+        w.w = __ballot_sync(0xffffffffu, px < p.HW && v.w > 0.5f);
+        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
+      }
+    }
+    __syncthreads();
+    // every warp has consumed stage `st`: refill it with chunk i + kStages while phase B runs
+    if (warp == 0 && i + kStages < nchunks) produce(i + kStages);
+    // ---- phase B: 16 warps = 8 words x 2 halves of the template rows ---------------------------------------
+    {
+      const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
+      if (half == 0) {
+        area0 += __popc(b0);
+        area1 += __popc(b1);
+      }
+#pragma unroll
+      for (int o = 0; o < TH; ++o) {
+        const uint32_t a = bits[buf][grp_b][pcnt + half * TH + o][word_b];
+        acc[o][0] += __popc(a & b0);
+        acc[o][1] += __popc(a & b1);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int o = 0; o < TH; ++o) {
+    const int oo = half * TH + o;
+    if (oo < ocnt) {
+      atomicAdd(&red[oo * kMaxRows + lane], acc[o][0]);
+      atomicAdd(&red[oo * kMaxRows + lane + 32], acc[o][1]);
+    }
+  }
+  if (half == 0) {
+    atomicAdd(&red[kTileO * kMaxRows + lane], area0);
+    atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
+  }
+  __syncthreads();
+
+  int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
+  for (int i = tid; i < ocnt * pcnt; i += kTmaThreads) {
+    const int o = i / pcnt, q = i - o * pcnt;
+    out[(o0 + o) * p.P + p0 + q] = red[o * kMaxRows + q];
+  }
+  int* area_t = out + p.Otot * p.P;
+  int* area_p = area_t + p.Otot;
+  if (ptile == 0)
+    for (int i = tid; i < ocnt; i += kTmaThreads) area_t[o0 + i] = red[kTileO * kMaxRows + pcnt + i];
+  if (otile == 0)
+    for (int i = tid; i < pcnt; i += kTmaThreads) area_p[p0 + i] = red[kTileO * kMaxRows + i];
+}
+
+template <int TO>
+int launch_tma(const IouParams& kp, dim3 grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(mask_iou_partial_tma_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kTmaDynSmem);
+  if (e != cudaSuccess) { set_last_cuda_error((int)e); return DMM_ERR_CUDA; }
+  mask_iou_partial_tma_kernel<TO><<<grid, kTmaThreads, kTmaDynSmem, st>>>(kp);
+  return check_launch();
+}
+
 struct FinParams {
   const int* ws;
   int S, cnt, B, P, O, Otot;
@@ -308,17 +512,26 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
   const bool vec = (HW % 4 == 0) && aligned16(prop) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
                    (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
   dim3 grid(pl.S, B, pl.n_ptiles * pl.n_otiles);
-#define DMM_LAUNCH(V, T) mask_iou_partial_kernel<V, T><<<grid, kThreads, 0, st>>>(kp)
   const int to = pl.OT <= 4 ? 4 : (pl.OT <= 8 ? 8 : (pl.OT <= 12 ? 12 : 16));
-  if (vec) {
-    if (to == 4) DMM_LAUNCH(true, 4); else if (to == 8) DMM_LAUNCH(true, 8);
-    else if (to == 12) DMM_LAUNCH(true, 12); else DMM_LAUNCH(true, 16);
+  // DMM_K1_IMPL=ldg|tma selects the staging path (read-only environment lookup; default chosen by measurement)
+  const char* impl = getenv("DMM_K1_IMPL");
+  const bool use_tma = vec && impl && impl[0] == 't';
+  int rc;
+  if (use_tma) {
+    rc = to == 4 ? launch_tma<4>(kp, grid, st) : to == 8 ? launch_tma<8>(kp, grid, st)
+       : to == 12 ? launch_tma<12>(kp, grid, st) : launch_tma<16>(kp, grid, st);
   } else {
-    if (to == 4) DMM_LAUNCH(false, 4); else if (to == 8) DMM_LAUNCH(false, 8);
-    else if (to == 12) DMM_LAUNCH(false, 12); else DMM_LAUNCH(false, 16);
-  }
+#define DMM_LAUNCH(V, T) mask_iou_partial_kernel<V, T><<<grid, kThreads, 0, st>>>(kp)
+    if (vec) {
+      if (to == 4) DMM_LAUNCH(true, 4); else if (to == 8) DMM_LAUNCH(true, 8);
+      else if (to == 12) DMM_LAUNCH(true, 12); else DMM_LAUNCH(true, 16);
+    } else {
+      if (to == 4) DMM_LAUNCH(false, 4); else if (to == 8) DMM_LAUNCH(false, 8);
+      else if (to == 12) DMM_LAUNCH(false, 12); else DMM_LAUNCH(false, 16);
+    }
 #undef DMM_LAUNCH
-  int rc = check_launch();
+    rc = check_launch();
+  }
   if (rc) return rc;
 
   FinParams fp;
