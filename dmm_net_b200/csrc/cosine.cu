@@ -75,7 +75,12 @@ __global__ void __launch_bounds__(kThreads) cosine_fwd_kernel(const CosParams p)
         for (int r = 0; r < kRowTile; ++r)
           if (r < ro) {
             const float s = warp_sum(acc[r]);
-            if (lane == 0) cosb[(o0 + r) * p.P + c] += s;  // this warp is the only writer of column c
+            // this warp is the only writer of column c; the first template set stores (a read-modify-write here is a
+            // dependent ~0.7 us global round trip per entry: it made this kernel 60 us at B=64), later sets accumulate
+            if (lane == 0) {
+              if (t == 0) cosb[(o0 + r) * p.P + c] = s;
+              else cosb[(o0 + r) * p.P + c] += s;
+            }
           }
       }
     }

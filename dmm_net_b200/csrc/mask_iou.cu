@@ -9,6 +9,8 @@
 //     broadcasts: popc(a & b) into O x 2 register counters per lane;
 //   - per-slab int32 partials go to a workspace (no atomics, no memset), a second tiny kernel adds the
 //     slabs and forms  inter / (float(|A|+|B|-inter) + 1e-6f)  -- integer-exact, so bit-equal to the reference.
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -192,20 +194,25 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
 }
 
 // =========================================================================================================
-// K1, TMA variant: the same computation with the row pieces staged by the TMA engine.
-//   - rows are contiguous 1-D runs, so the copy is cp.async.bulk (SASS UBLKCP) global -> shared, one per row piece,
-//     completing on an mbarrier with expect_tx: a kStages-deep ring of [64 rows][256 px] fp32 stages (64 KB each);
-//   - no register staging: 16 consumer warps read the landed stage with conflict-free LDS.128, ballot, popcount;
-//   - stage reuse needs no "empty" barrier: a stage is refilled right after the __syncthreads() that follows the
-//     last read of it (the reads have retired: their values fed the ballots).
-// Requires 16-byte aligned rows (HW % 4 == 0), like the vector path; the LDG kernel covers everything else.
+// K1, TMA variant: the same computation with the mask tiles staged by the TMA engine.
+//   - three tensor maps (proposals, templates, optional targets) describe the [B][rows][HW] fp32 tensors; ONE
+//     cp.async.bulk.tensor.3d (SASS UTMALDG) per tensor and chunk copies a [rows x 256 px] box into a 64 KB stage
+//     and completes on an mbarrier (expect_tx); pixels past the row end are zero-filled by the TMA (no tail path);
+//   - warp-specialised: one producer warp (a single elected lane) runs ahead through a kStages-deep ring guarded
+//     by full/empty mbarriers; 16 consumer warps read the landed stage with conflict-free LDS.128, ballot the
+//     threshold into bit planes and popcount -- no register staging, no scoreboard coupling to the loads;
+//   - consumers synchronise among themselves with a named barrier; the producer never joins it.
+// Requires 16-byte aligned rows (HW % 4 == 0) and a single tile (P + Otot <= 64, Otot <= 16): the common case.
+// (First attempt, kept in profiles/r1_k1_ncu_tma_v0.txt: per-row cp.async.bulk issued by 32 lanes of a consumer
+//  warp -- UBLKCP is a uniform-datapath instruction, the 64 copies per stage serialised on the critical path: 3.5 TB/s.)
 // =========================================================================================================
-constexpr int kTmaThreads = 512;
-constexpr int kTmaWarps = kTmaThreads / 32;
+constexpr int kTmaConsWarps = 16;
+constexpr int kTmaConsThreads = kTmaConsWarps * 32;
+constexpr int kTmaThreads = kTmaConsThreads + 32;                 // + one producer warp
 constexpr int kStages = 3;
 constexpr int kStageFloats = kMaxRows * kChunkPx;                 // 64 KB per stage
-constexpr size_t kTmaDynSmem = (size_t)kStages * kStageFloats * sizeof(float);
-constexpr int kTmaUnits = kMaxRows * 2 / kTmaWarps;               // 8 row pieces per warp per chunk
+constexpr size_t kTmaDynSmem = (size_t)kStages * kStageFloats * sizeof(float) + 128;
+constexpr int kTmaUnits = kMaxRows * 2 / kTmaConsWarps;           // 8 row pieces per warp per chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -214,10 +221,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -232,72 +237,66 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsThreads) : "memory"); }
 
 template <int TO>
-__global__ void __launch_bounds__(kTmaThreads, 1) mask_iou_partial_tma_kernel(const IouParams p) {
+__global__ void __launch_bounds__(kTmaThreads, 1)
+mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorMap tm_prop,
+                            const __grid_constant__ CUtensorMap tm_tmpl, const __grid_constant__ CUtensorMap tm_tmpl2) {
   constexpr int TH = TO / 2;                                      // template counters per warp half
-  extern __shared__ __align__(128) float stage[];                 // [kStages][kMaxRows][kChunkPx]
-  __shared__ const float* row_ptr[kMaxRows];
-  __shared__ uint32_t row_ok[kMaxRows];
+  extern __shared__ unsigned char smem_raw[];
+  float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   __shared__ uint32_t bits[2][2][kMaxRows + kTileO][4];
   __shared__ int red[kTileO * kMaxRows + kMaxRows];
   __shared__ __align__(8) unsigned long long full_bar[kStages];
+  __shared__ __align__(8) unsigned long long empty_bar[kStages];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.x, b = blockIdx.y;
-  const int ptile = blockIdx.z % p.n_ptiles, otile = blockIdx.z / p.n_ptiles;
-  const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
-  const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
-  const int p0 = ptile * p.PT, o0 = otile * p.OT;
-  const int pcnt = min(p.PT, p.P - p0), ocnt = min(p.OT, p.Otot - o0);
-  const int rows = pcnt + ocnt;
+  const int pcnt = p.P, ocnt = p.Otot;                            // single tile (checked on the host)
+  const bool two = p.tmpl2 != nullptr;
 
-  if (tid < kMaxRows) {
-    const float* ptr = nullptr;
-    if (tid < pcnt) {
-      if (p0 + tid < np) ptr = p.prop + (long long)b * p.prop_bs + (long long)(p0 + tid) * p.HW;
-    } else if (tid < rows) {
-      const int t = o0 + tid - pcnt;
-      if (t < p.O) {
-        if (t < nt) ptr = p.tmpl + (long long)b * p.tmpl_bs + (long long)t * p.HW;
-      } else if (t - p.O < nt) {
-        ptr = p.tmpl2 + (long long)b * p.tmpl2_bs + (long long)(t - p.O) * p.HW;
-      }
-    }
-    row_ptr[tid] = ptr;
-    row_ok[tid] = ptr != nullptr;
-  }
   for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kTmaThreads) red[i] = 0;
   if (tid == 0) {
 #pragma unroll
-    for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(&full_bar[st]), 1);
+    for (int st = 0; st < kStages; ++st) {
+      mbar_init(smem_u32(&full_bar[st]), 1);
+      mbar_init(smem_u32(&empty_bar[st]), kTmaConsWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  __syncthreads();   // the only CTA-wide barrier: the producer warp never joins another one
 
   const int c0 = s * p.chunks_per_slab;
   const int c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
   const int nchunks = max(c1 - c0, 0);
-  const int tail_chunk = (p.HW % kChunkPx) ? p.n_chunks - 1 : -1;
 
-  // producer = warp 0: lane 0 arms the barrier with the stage's byte count, then every lane copies its rows
-  const uint32_t ok0 = row_ok[lane], ok1 = row_ok[lane + 32];
-  const int nvalid = __popc(__ballot_sync(0xffffffffu, ok0)) + __popc(__ballot_sync(0xffffffffu, ok1));
-  auto produce = [&](int i) {
-    const int st = i % kStages;
-    const int px0 = (c0 + i) * kChunkPx;
-    const uint32_t bytes = (uint32_t)min(kChunkPx, p.HW - px0) * 4u;
-    const uint32_t bar = smem_u32(&full_bar[st]);
-    if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)nvalid);
-    __syncwarp();
-    float* dst = stage + (size_t)st * kStageFloats;
-    if (ok0) bulk_g2s(smem_u32(dst + lane * kChunkPx), row_ptr[lane] + px0, bytes, bar);
-    if (ok1) bulk_g2s(smem_u32(dst + (lane + 32) * kChunkPx), row_ptr[lane + 32] + px0, bytes, bar);
-  };
-  if (warp == 0) {
-    for (int i = 0; i < kStages && i < nchunks; ++i) produce(i);
+  if (warp == kTmaConsWarps) {
+    // ---- producer: one elected lane keeps the ring full --------------------------------------------------
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(pcnt + ocnt) * kChunkPx * 4u;   // full boxes: OOB pixels are zero-filled
+      for (int i = 0; i < nchunks; ++i) {
+        const int st = i % kStages;
+        if (i >= kStages) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((i / kStages) - 1) & 1));
+        const uint32_t bar = smem_u32(&full_bar[st]);
+        const uint32_t dst = smem_u32(stage + (size_t)st * kStageFloats);
+        const int px0 = (c0 + i) * kChunkPx;
+        mbar_expect_tx(bar, bytes);
+        tma_load_3d(dst, &tm_prop, px0, 0, b, bar);
+        tma_load_3d(dst + (uint32_t)pcnt * kChunkPx * 4u, &tm_tmpl, px0, 0, b, bar);
+        if (two) tma_load_3d(dst + (uint32_t)(pcnt + p.O) * kChunkPx * 4u, &tm_tmpl2, px0, 0, b, bar);
+      }
+    }
+    return;
   }
 
+  // ---- consumers ---------------------------------------------------------------------------------------------
   int acc[TH][2];
 #pragma unroll
   for (int o = 0; o < TH; ++o) acc[o][0] = acc[o][1] = 0;
@@ -307,40 +306,25 @@ __global__ void __launch_bounds__(kTmaThreads, 1) mask_iou_partial_tma_kernel(co
   const int lane_px = lane * 4;
 
   for (int i = 0; i < nchunks; ++i) {
-    const int c = c0 + i, st = i % kStages, buf = i & 1;
+    const int st = i % kStages, buf = i & 1;
     mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((i / kStages) & 1));
     const float* sbase = stage + (size_t)st * kStageFloats;
     // ---- phase A: landed stage -> bit planes (8 row pieces per warp) --------------------------------------
-    if (c != tail_chunk) {
+    // rows >= pcnt+ocnt of the stage are never written by the TMA: stale bits, counted into counters nobody reads
 #pragma unroll
-      for (int k = 0; k < kTmaUnits; ++k) {
-        const int u = warp + kTmaWarps * k;
-        const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
-        uint4 w;
-        w.x = __ballot_sync(0xffffffffu, v.x > 0.5f);
-        w.y = __ballot_sync(0xffffffffu, v.y > 0.5f);
-        w.z = __ballot_sync(0xffffffffu, v.z > 0.5f);
-        w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
-        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
-      }
-    } else {
-      const int base = c * kChunkPx + lane_px;
-#pragma unroll
-      for (int k = 0; k < kTmaUnits; ++k) {
-        const int u = warp + kTmaWarps * k;
-        const int px = base + (u & 1) * 128;
-        const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
-        uint4 w;   // bytes past the row end were not copied: stale smem, masked here (HW % 4 == 0: all four together)
-        w.x = __ballot_sync(0xffffffffu, px < p.HW && v.x > 0.5f);
-        w.y = __ballot_sync(0xffffffffu, px < p.HW && v.y > 0.5f);
-        w.z = __ballot_sync(0xffffffffu, px < p.HW && v.z > 0.5f);
-        w.w = __ballot_sync(0xffffffffu, px < p.HW && v.w > 0.5f);
-        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
-      }
+    for (int k = 0; k < kTmaUnits; ++k) {
+      const int u = warp + kTmaConsWarps * k;
+      const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
+      uint4 w;
+      w.x = __ballot_sync(0xffffffffu, v.x > 0.5f);
+      w.y = __ballot_sync(0xffffffffu, v.y > 0.5f);
+      w.z = __ballot_sync(0xffffffffu, v.z > 0.5f);
+      w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
+      *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
     }
-    __syncthreads();
-    // every warp has consumed stage `st`: refill it with chunk i + kStages while phase B runs
-    if (warp == 0 && i + kStages < nchunks) produce(i + kStages);
+    // this warp is done with the stage (its loads fed the ballots above): hand it back to the producer
+    if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
+    consumer_barrier();
     // ---- phase B: 16 warps = 8 words x 2 halves of the template rows ---------------------------------------
     {
       const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
@@ -355,6 +339,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) mask_iou_partial_tma_kernel(co
         acc[o][1] += __popc(a & b1);
       }
     }
+    // double-buffered bit planes: buffer `buf` is rewritten in iteration i+2, after the barrier of iteration i+1
   }
 
 #pragma unroll
@@ -369,27 +354,58 @@ __global__ void __launch_bounds__(kTmaThreads, 1) mask_iou_partial_tma_kernel(co
     atomicAdd(&red[kTileO * kMaxRows + lane], area0);
     atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
   }
-  __syncthreads();
+  consumer_barrier();
 
   int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
-  for (int i = tid; i < ocnt * pcnt; i += kTmaThreads) {
+  for (int i = tid; i < ocnt * pcnt; i += kTmaConsThreads) {
     const int o = i / pcnt, q = i - o * pcnt;
-    out[(o0 + o) * p.P + p0 + q] = red[o * kMaxRows + q];
+    out[o * p.P + q] = red[o * kMaxRows + q];
   }
   int* area_t = out + p.Otot * p.P;
   int* area_p = area_t + p.Otot;
-  if (ptile == 0)
-    for (int i = tid; i < ocnt; i += kTmaThreads) area_t[o0 + i] = red[kTileO * kMaxRows + pcnt + i];
-  if (otile == 0)
-    for (int i = tid; i < pcnt; i += kTmaThreads) area_p[p0 + i] = red[kTileO * kMaxRows + i];
+  for (int i = tid; i < ocnt; i += kTmaConsThreads) area_t[i] = red[kTileO * kMaxRows + pcnt + i];
+  for (int i = tid; i < pcnt; i += kTmaConsThreads) area_p[i] = red[kTileO * kMaxRows + i];
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) -------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static const EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      ptr = nullptr;
+    }
+    return (EncodeTiledFn)ptr;
+  }();
+  return fn;
+}
+
+// [B][rows][HW] fp32 with batch stride `bs` elements; box = [1][rows][256 px]
+bool make_map(CUtensorMap* m, const float* base, long long bs, int B, int rows, int HW) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)rows, (cuuint64_t)B};
+  const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4ull, (cuuint64_t)(B > 1 ? bs : (long long)rows * HW) * 4ull};
+  const cuuint32_t box[3] = {(cuuint32_t)kChunkPx, (cuuint32_t)rows, 1u};
+  const cuuint32_t es[3] = {1u, 1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int TO>
-int launch_tma(const IouParams& kp, dim3 grid, cudaStream_t st) {
+int launch_tma(const IouParams& kp, const CUtensorMap& mp, const CUtensorMap& mt, const CUtensorMap& mt2, dim3 grid,
+               cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(mask_iou_partial_tma_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kTmaDynSmem);
   if (e != cudaSuccess) { set_last_cuda_error((int)e); return DMM_ERR_CUDA; }
-  mask_iou_partial_tma_kernel<TO><<<grid, kTmaThreads, kTmaDynSmem, st>>>(kp);
+  mask_iou_partial_tma_kernel<TO><<<grid, kTmaThreads, kTmaDynSmem, st>>>(kp, mp, mt, mt2);
   return check_launch();
 }
 
@@ -515,11 +531,17 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
   const int to = pl.OT <= 4 ? 4 : (pl.OT <= 8 ? 8 : (pl.OT <= 12 ? 12 : 16));
   // DMM_K1_IMPL=ldg|tma selects the staging path (read-only environment lookup; default chosen by measurement)
   const char* impl = getenv("DMM_K1_IMPL");
-  const bool use_tma = vec && impl && impl[0] == 't';
+  bool use_tma = vec && impl && impl[0] == 't' && pl.n_ptiles == 1 && pl.n_otiles == 1 && HW >= kChunkPx;
+  CUtensorMap mp, mt, mt2;
+  if (use_tma) {
+    use_tma = make_map(&mp, prop, prop_bstride, B, P, HW) && make_map(&mt, tmpl, tmpl_bstride, B, O, HW);
+    if (use_tma && two) use_tma = make_map(&mt2, tmpl2, tmpl2_bstride, B, O, HW);
+    if (use_tma && !two) mt2 = mt;
+  }
   int rc;
   if (use_tma) {
-    rc = to == 4 ? launch_tma<4>(kp, grid, st) : to == 8 ? launch_tma<8>(kp, grid, st)
-       : to == 12 ? launch_tma<12>(kp, grid, st) : launch_tma<16>(kp, grid, st);
+    rc = to == 4 ? launch_tma<4>(kp, mp, mt, mt2, grid, st) : to == 8 ? launch_tma<8>(kp, mp, mt, mt2, grid, st)
+       : to == 12 ? launch_tma<12>(kp, mp, mt, mt2, grid, st) : launch_tma<16>(kp, mp, mt, mt2, grid, st);
   } else {
 #define DMM_LAUNCH(V, T) mask_iou_partial_kernel<V, T><<<grid, kThreads, 0, st>>>(kp)
     if (vec) {
