@@ -529,9 +529,11 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
                    (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
   dim3 grid(pl.S, B, pl.n_ptiles * pl.n_otiles);
   const int to = pl.OT <= 4 ? 4 : (pl.OT <= 8 ? 8 : (pl.OT <= 12 ? 12 : 16));
-  // DMM_K1_IMPL=ldg|tma selects the staging path (read-only environment lookup; default chosen by measurement)
+  // Staging path: the TMA ring is the default whenever it applies (aligned rows, single tile, tensor maps available);
+  // measured on par with / slightly ahead of the LDG pipeline (profiles/README.md).  DMM_K1_IMPL=ldg forces the
+  // LDG kernel (read-only environment lookup, used by the A/B parity test).
   const char* impl = getenv("DMM_K1_IMPL");
-  bool use_tma = vec && impl && impl[0] == 't' && pl.n_ptiles == 1 && pl.n_otiles == 1 && HW >= kChunkPx;
+  bool use_tma = vec && !(impl && impl[0] == 'l') && pl.n_ptiles == 1 && pl.n_otiles == 1 && HW >= kChunkPx;
   CUtensorMap mp, mt, mt2;
   if (use_tma) {
     use_tma = make_map(&mp, prop, prop_bstride, B, P, HW) && make_map(&mt, tmpl, tmpl_bstride, B, O, HW);
