@@ -83,6 +83,31 @@ __global__ void __launch_bounds__(kThreads) assign_apply_kernel(const ApplyParam
     if (o < 0 && !p.zero_fill) continue;
     float* orow = outb + (long long)f * p.HW;
     const int cnt = o < 0 ? 0 : (dense ? n_in : nz_cnt[o]);
+    if (VEC && !dense && cnt == 1) {
+      // the common inference case (one selected proposal per template): a scaled streaming copy, 4 loads in flight
+      const float v = nz_val[o][0];
+      const int c = nz_idx[o][0];
+      const float* src = inb + (long long)(imap ? imap[c] : c) * p.HW;
+      int q = q0 + tid;
+      for (; q + 3 * kThreads < q1; q += 4 * kThreads) {
+        float4 m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = ld_stream_f4(src + 4 * (q + k * kThreads));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          st_stream_f4(orow + 4 * (q + k * kThreads), make_float4(v * m[k].x, v * m[k].y, v * m[k].z, v * m[k].w));
+      }
+      for (; q < q1; q += kThreads) {
+        const float4 m = ld_stream_f4(src + 4 * q);
+        st_stream_f4(orow + 4 * q, make_float4(v * m.x, v * m.y, v * m.z, v * m.w));
+      }
+      continue;
+    }
+    if (VEC && cnt == 0) {
+      int q = q0 + tid;
+      for (; q < q1; q += kThreads) st_stream_f4(orow + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
     for (int q = q0 + tid; q < q1; q += kThreads) {
       if (VEC) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);

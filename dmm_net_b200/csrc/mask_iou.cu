@@ -524,6 +524,9 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
   kp.S = pl.S; kp.chunks_per_slab = pl.chunks_per_slab; kp.n_chunks = pl.n_chunks;
   kp.ws = (int*)workspace; kp.cnt = pl.cnt;
 
+  if (HW == 0) {  // empty masks: every count is 0 -> IoU 0/(0+1e-6) = 0; skip the streaming kernel
+    DMM_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)B * pl.S * pl.cnt * sizeof(int), st));
+  }
   auto aligned16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
   const bool vec = (HW % 4 == 0) && aligned16(prop) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
                    (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
@@ -540,8 +543,9 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
     if (use_tma && two) use_tma = make_map(&mt2, tmpl2, tmpl2_bstride, B, O, HW);
     if (use_tma && !two) mt2 = mt;
   }
-  int rc;
-  if (use_tma) {
+  int rc = DMM_OK;
+  if (HW == 0) {
+  } else if (use_tma) {
     rc = to == 4 ? launch_tma<4>(kp, mp, mt, mt2, grid, st) : to == 8 ? launch_tma<8>(kp, mp, mt, mt2, grid, st)
        : to == 12 ? launch_tma<12>(kp, mp, mt, mt2, grid, st) : launch_tma<16>(kp, mp, mt, mt2, grid, st);
   } else {

@@ -60,14 +60,17 @@ def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[to
     tmpl = _cuda_f32(tmpl, "tmpl")
     B, P = prop.shape[:2]
     O = tmpl.shape[1]
-    prop = prop.reshape(B, P, -1)
-    tmpl = tmpl.reshape(B, O, -1)
-    HW = prop.shape[2]
-    assert tmpl.shape[0] == B and tmpl.shape[2] == HW, (prop.shape, tmpl.shape)
+    HW = 1
+    for dsz in prop.shape[2:]:
+        HW *= int(dsz)
+    prop = prop.reshape(B, P, HW)
+    assert tmpl.shape[0] == B and tmpl.numel() == B * O * HW, (prop.shape, tmpl.shape)
+    tmpl = tmpl.reshape(B, O, HW)
     dev = prop.device
     if tmpl2 is not None:
-        tmpl2 = _cuda_f32(tmpl2, "tmpl2").reshape(B, O, -1)
-        assert tmpl2.shape == tmpl.shape
+        tmpl2 = _cuda_f32(tmpl2, "tmpl2")
+        assert tmpl2.numel() == tmpl.numel(), (tmpl2.shape, tmpl.shape)
+        tmpl2 = tmpl2.reshape(B, O, HW)
     n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
     iou = torch.empty(B, O, P, device=dev)
     iou2 = torch.empty(B, O, P, device=dev) if tmpl2 is not None else None

@@ -333,3 +333,27 @@ def test_k1_tma_and_ldg_variants_agree_bit_exact(monkeypatch, P, O, H, W):
         want = orc.pairwise_binary_iou(pr.prop_mask[b, :p].reshape(p, -1), pr.tmpl_mask[b, :o].reshape(o, -1), expand=False)
         np.testing.assert_array_equal(res["tma"]["iou"][b, :o, :p].cpu().numpy(), want.numpy())
         assert res["tma"]["iou"][b, o:].abs().sum() == 0 and res["tma"]["iou"][b, :, p:].abs().sum() == 0
+
+
+def test_edge_empty_and_tiny_inputs():
+    """Empty batch, zero pixels, a single pixel, one proposal: defined outputs, no out-of-bounds reads."""
+    z = ops.mask_iou_pairwise(torch.zeros(0, 5, 16, device=DEV), torch.zeros(0, 2, 16, device=DEV))
+    assert z["iou"].shape == (0, 2, 5)
+    e = ops.mask_iou_pairwise(torch.zeros(2, 5, 0, device=DEV), torch.zeros(2, 3, 0, device=DEV))
+    assert e["iou"].shape == (2, 3, 5) and float(e["iou"].abs().sum()) == 0.0
+    one = ops.mask_iou_pairwise(torch.ones(1, 1, 1, device=DEV), torch.ones(1, 1, 1, device=DEV))["iou"]
+    assert abs(float(one) - 1.0 / (1.0 + 1e-6)) < 1e-7
+    four = ops.mask_iou_pairwise(torch.ones(1, 2, 4, device=DEV), torch.tensor([[[1., 0, 1, 0]]], device=DEV))["iou"]
+    np.testing.assert_array_equal(four.cpu().numpy(), np.float32([[[2 / (4 + 1e-6), 2 / (4 + 1e-6)]]]))
+    # a single proposal against several templates takes the pad rule (m = O + 1)
+    pr = make_problem(1, 3, 8, 12, 16, config=5, index=0)
+    cfg = default_cfg(20, 5)
+    d = pr.to(DEV)
+    with torch.no_grad():
+        got = MatchModel(cfg, 1)(d.prop_feat, d.prop_mask, [d.tmpl_feat], d.tmpl_mask, d.prop_score)
+        L = int(MatchModel(cfg, 1).forward_many(d.prop_feat[None], d.prop_mask[None], d.tmpl_feat[None], d.tmpl_mask[None],
+                                                d.prop_score[None])["n_list"][0])
+    want = orc.match_layer_forward(cfg, 1, pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, pr.prop_score,
+                                   force_len=L)
+    for a, b, n in zip(got[:3], want[:3], ("full_outmask", "match_score", "det_score")):
+        close(a, b, TOL, n)
