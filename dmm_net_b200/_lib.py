@@ -24,6 +24,8 @@ SIGNATURES = {
     "dmm_mask_iou_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "dmm_mask_iou_pairwise": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp,
                                    _vp, _vp, _sz, _vp]),
+    "dmm_mask_iou_pairwise_ptrs": (_i, [_vp, _i, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp,
+                                        _vp, _vp, _sz, _vp]),
     "dmm_mask_iou_rowwise_workspace_bytes": (_sz, [_i, _i]),
     "dmm_mask_iou_rowwise": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dmm_cosine_pairwise": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp]),
@@ -34,6 +36,8 @@ SIGNATURES = {
     "dmm_relax_solve_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i,
                                  _f, _i, _i, _vp, _vp, _vp]),
     "dmm_assign_apply": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp]),
+    "dmm_assign_apply_ptrs": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp]),
+    "dmm_assign_apply_bwd_ptrs": (_i, [_vp, _ll, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dmm_assign_apply_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "dmm_assign_apply_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                   _vp]),

@@ -21,6 +21,7 @@ struct ApplyParams {
   long long coef_bs;
   int coef_rs, coef_cs;         // element strides of (out row, in row) inside one problem's matrix
   const float* in;              // [B][*][HW]
+  const float* const* in_ptrs;  // optional per-problem base pointers; overrides in/in_bs
   long long in_bs;
   float* out;                   // [B][n_out_rows][HW]
   long long out_bs;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) assign_apply_kernel(const ApplyParam
   __syncthreads();
   const bool dense = overflow != 0;               // rare: a row with more than kCap non-zeros -> read coefficients directly
 
-  const float* inb = p.in + (long long)b * p.in_bs;
+  const float* inb = p.in_ptrs ? p.in_ptrs[b] : p.in + (long long)b * p.in_bs;
   float* outb = p.out + (long long)b * p.out_bs;
   const int* imap = p.in_map ? p.in_map + (long long)b * p.n_in_max : nullptr;
   const int step = VEC ? 4 : 1;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kThreads) assign_apply_kernel(const ApplyParam
 struct ApplyBwdParams {
   const float* gout; long long gout_bs;
   const float* prop; long long prop_bs;
+  const float* const* prop_ptrs;
   const float* logic;           // [B][O][MS]
   const int* row_map;
   const int* n_prop; const int* n_tmpl;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) assign_apply_bwd_partial_kernel(cons
   const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
   const float* logic = p.logic + (long long)b * p.O * p.MS;
   const float* goutb = p.gout + (long long)b * p.gout_bs;
-  const float* propb = p.prop + (long long)b * p.prop_bs;
+  const float* propb = p.prop_ptrs ? p.prop_ptrs[b] : p.prop + (long long)b * p.prop_bs;
   float* part = p.partial + ((long long)b * p.S + s) * p.O * p.MS;
   const int step = VEC ? 4 : 1;
   const int nq = (p.HW + step - 1) / step;
@@ -213,25 +215,41 @@ inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
 
 using namespace dmm;
 
-extern "C" int dmm_assign_apply(const float* Bmat, const float* prop, long long prop_bstride, int B, int P, int O,
-                                int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map, int O_out,
-                                int zero_fill, float* out, long long out_bstride, void* stream) {
+static int run_apply(const float* Bmat, const float* prop, const float* const* prop_ptrs, int ptrs_aligned16,
+                     long long prop_bstride, int B, int P, int O, int MS, int HW, const int* n_prop, const int* n_tmpl,
+                     const int* row_map, int O_out, int zero_fill, float* out, long long out_bstride, void* stream) {
   if (B < 0 || P < 0 || O < 0 || HW < 0 || MS < P || O_out < 0) return DMM_ERR_INVALID_ARGUMENT;
   if (B == 0 || O_out == 0 || HW == 0) return DMM_OK;
   if (!out) return DMM_ERR_INVALID_ARGUMENT;
-  if ((O > 0 && P > 0) && (!Bmat || !prop)) return DMM_ERR_INVALID_ARGUMENT;
+  if ((O > 0 && P > 0) && (!Bmat || (!prop && !prop_ptrs))) return DMM_ERR_INVALID_ARGUMENT;
   if (P > kMaxIn || O > kMaxOut || O_out > kMaxOut || B > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
   ApplyParams kp;
   kp.coef = Bmat; kp.coef_bs = (long long)O * MS; kp.coef_rs = MS; kp.coef_cs = 1;
-  kp.in = prop; kp.in_bs = prop_bstride; kp.out = out; kp.out_bs = out_bstride;
+  kp.in = prop; kp.in_ptrs = prop_ptrs; kp.in_bs = prop_bstride; kp.out = out; kp.out_bs = out_bstride;
   kp.in_map = nullptr; kp.out_map = row_map; kp.n_in_arr = n_prop; kp.n_out_arr = n_tmpl;
   kp.n_in_max = P; kp.n_out_max = O; kp.out_rows_phys = O_out; kp.zero_fill = zero_fill;
   kp.B = B; kp.HW = HW; kp.S = pick_slabs(B, HW);
-  const bool vec = HW % 4 == 0 && aligned16(prop) && aligned16(out) && prop_bstride % 4 == 0 && out_bstride % 4 == 0;
+  const bool vec = HW % 4 == 0 && (prop_ptrs ? ptrs_aligned16 != 0 : (aligned16(prop) && prop_bstride % 4 == 0)) &&
+                   aligned16(out) && out_bstride % 4 == 0;
   dim3 grid(kp.S, B);
   if (vec) assign_apply_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(kp);
   else assign_apply_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(kp);
   return check_launch();
+}
+
+extern "C" int dmm_assign_apply(const float* Bmat, const float* prop, long long prop_bstride, int B, int P, int O,
+                                int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map, int O_out,
+                                int zero_fill, float* out, long long out_bstride, void* stream) {
+  return run_apply(Bmat, prop, nullptr, 0, prop_bstride, B, P, O, MS, HW, n_prop, n_tmpl, row_map, O_out, zero_fill, out,
+                   out_bstride, stream);
+}
+
+extern "C" int dmm_assign_apply_ptrs(const float* Bmat, const float* const* prop_ptrs, int ptrs_aligned16, int B, int P,
+                                     int O, int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map,
+                                     int O_out, int zero_fill, float* out, long long out_bstride, void* stream) {
+  if (!prop_ptrs) return DMM_ERR_INVALID_ARGUMENT;
+  return run_apply(Bmat, nullptr, prop_ptrs, ptrs_aligned16, 0, B, P, O, MS, HW, n_prop, n_tmpl, row_map, O_out,
+                   zero_fill, out, out_bstride, stream);
 }
 
 extern "C" size_t dmm_assign_apply_bwd_workspace_bytes(int B, int P, int O, int HW) {
@@ -240,20 +258,21 @@ extern "C" size_t dmm_assign_apply_bwd_workspace_bytes(int B, int P, int O, int 
   return align_up((size_t)B * pick_slabs(B, HW) * O * MS * sizeof(float), 256);
 }
 
-extern "C" int dmm_assign_apply_bwd(const float* g_out, long long gout_bstride, const float* prop,
-                                    long long prop_bstride, const float* Bmat, const float* logic, int B, int P,
-                                    int O, int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map,
-                                    float* g_Bmat, float* g_prop, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
+static int run_apply_bwd(const float* g_out, long long gout_bstride, const float* prop, const float* const* prop_ptrs,
+                         int ptrs_aligned16, long long prop_bstride, const float* Bmat, const float* logic, int B, int P,
+                         int O, int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map, float* g_Bmat,
+                         float* g_prop, void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 0 || P < 0 || O < 0 || HW < 0 || MS < P) return DMM_ERR_INVALID_ARGUMENT;
   if (B == 0 || O == 0 || P == 0) return DMM_OK;
-  if (!g_out || !prop || !logic) return DMM_ERR_INVALID_ARGUMENT;
+  if (!g_out || (!prop && !prop_ptrs) || !logic) return DMM_ERR_INVALID_ARGUMENT;
   if (P > kMaxIn || O > kMaxOut || B > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec = HW % 4 == 0 && aligned16(prop) && aligned16(g_out) && prop_bstride % 4 == 0 && gout_bstride % 4 == 0;
+  const bool vec = HW % 4 == 0 && (prop_ptrs ? ptrs_aligned16 != 0 : (aligned16(prop) && prop_bstride % 4 == 0)) &&
+                   aligned16(g_out) && gout_bstride % 4 == 0;
   if (g_Bmat) {
     ApplyBwdParams kp;
-    kp.gout = g_out; kp.gout_bs = gout_bstride; kp.prop = prop; kp.prop_bs = prop_bstride; kp.logic = logic;
+    kp.gout = g_out; kp.gout_bs = gout_bstride; kp.prop = prop; kp.prop_ptrs = prop_ptrs; kp.prop_bs = prop_bstride;
+    kp.logic = logic;
     kp.row_map = row_map; kp.n_prop = n_prop; kp.n_tmpl = n_tmpl;
     kp.B = B; kp.P = P; kp.O = O; kp.MS = MS; kp.HW = HW; kp.S = pick_slabs(B, HW > 0 ? HW : 1);
     if (!workspace || workspace_bytes < (size_t)B * kp.S * O * MS * sizeof(float)) return DMM_ERR_WORKSPACE_TOO_SMALL;
@@ -274,7 +293,7 @@ extern "C" int dmm_assign_apply_bwd(const float* g_out, long long gout_bstride, 
     if (!Bmat) return DMM_ERR_INVALID_ARGUMENT;
     ApplyParams kp;
     kp.coef = Bmat; kp.coef_bs = (long long)O * MS; kp.coef_rs = 1; kp.coef_cs = MS;
-    kp.in = g_out; kp.in_bs = gout_bstride; kp.out = g_prop; kp.out_bs = (long long)P * HW;  // g_prop is dense [B][P][HW]
+    kp.in = g_out; kp.in_ptrs = nullptr; kp.in_bs = gout_bstride; kp.out = g_prop; kp.out_bs = (long long)P * HW;  // g_prop is dense [B][P][HW]
     kp.in_map = row_map; kp.out_map = nullptr; kp.n_in_arr = n_tmpl; kp.n_out_arr = n_prop;
     kp.n_in_max = O; kp.n_out_max = P; kp.out_rows_phys = P; kp.zero_fill = 1;
     kp.B = B; kp.HW = HW; kp.S = pick_slabs(B, HW > 0 ? HW : 1);
@@ -285,4 +304,23 @@ extern "C" int dmm_assign_apply_bwd(const float* g_out, long long gout_bstride, 
     return check_launch();
   }
   return DMM_OK;
+}
+
+extern "C" int dmm_assign_apply_bwd(const float* g_out, long long gout_bstride, const float* prop,
+                                    long long prop_bstride, const float* Bmat, const float* logic, int B, int P,
+                                    int O, int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map,
+                                    float* g_Bmat, float* g_prop, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  return run_apply_bwd(g_out, gout_bstride, prop, nullptr, 0, prop_bstride, Bmat, logic, B, P, O, MS, HW, n_prop, n_tmpl,
+                       row_map, g_Bmat, g_prop, workspace, workspace_bytes, stream);
+}
+
+/* g_prop is not offered here: per-video proposal tensors come from the (non-differentiable) proposal generator. */
+extern "C" int dmm_assign_apply_bwd_ptrs(const float* g_out, long long gout_bstride, const float* const* prop_ptrs,
+                                         int ptrs_aligned16, const float* Bmat, const float* logic, int B, int P, int O,
+                                         int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map,
+                                         float* g_Bmat, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!prop_ptrs) return DMM_ERR_INVALID_ARGUMENT;
+  return run_apply_bwd(g_out, gout_bstride, nullptr, prop_ptrs, ptrs_aligned16, 0, Bmat, logic, B, P, O, MS, HW, n_prop,
+                       n_tmpl, row_map, g_Bmat, nullptr, workspace, workspace_bytes, stream);
 }

@@ -36,59 +36,126 @@ __device__ __forceinline__ float row_norm(const float* v, int D, int lane) {
   return __fsqrt_rn(warp_sum(s));
 }
 
+// Forward, v2 (round 1: v1 made lanes walk D and re-derived every smem address per (row, d): 19.5 k warp-instructions
+// per warp, 55 us at B=64).  Now LANES ARE PROPOSALS: feature tiles of kDT columns are staged in shared memory with a
+// +1 padded pitch (conflict-free column walks), a warp task is (one template row or the norm row) x (32 proposals), the
+// template value is an smem broadcast: 2 LDS + 1 FFMA per (row, proposal, d).  The raw dot product and the squared
+// norms are accumulated in one pass; cos = dot / (max(|q|,eps) * max(|k|,eps)).
+constexpr int kDT = 64;                 // feature columns per tile
+constexpr int kPitch = kDT + 1;
+constexpr int kMaxP = 128;              // proposals per problem (solver limit)
+constexpr int kMaxTasks = (kRowTile + 1) * (kMaxP / 32);   // 68
+constexpr int kTPW = (kMaxTasks + kWarps - 1) / kWarps;    // 9 accumulators per lane at most
+
 __global__ void __launch_bounds__(kThreads) cosine_fwd_kernel(const CosParams p) {
-  extern __shared__ float qs[];  // [rt][D] normalised template rows
+  __shared__ float ks[kMaxP * kPitch];            // proposal feature tile   [np][kDT]
+  __shared__ float qs[kRowTile * kPitch];         // template feature tile   [ro][kDT]
+  __shared__ float knorm2[kMaxP];
+  __shared__ float qnorm[kRowTile];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
   const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
   const int D = p.D;
-  int rt = kSmemFloats / (D > 0 ? D : 1);
-  rt = rt > kRowTile ? kRowTile : (rt < 1 ? 1 : rt);
   float* cosb = p.cos + (long long)b * p.O * p.P;
-  for (int i = tid; i < p.O * p.P; i += kThreads) cosb[i] = 0.f;
-  __syncthreads();
   const float* kb = p.k + (long long)b * p.P * D;
-  for (int t = 0; t < p.T; ++t) {
-    const float* qb = p.q + ((long long)b * p.T + t) * p.O * D;
-    for (int o0 = 0; o0 < nt; o0 += rt) {
-      const int ro = min(rt, nt - o0);
+  const int npb = (np + 31) / 32;                 // proposal blocks of 32 lanes
+  const float invT = 1.f / (float)p.T;
+  for (int i = tid; i < p.O * p.P; i += kThreads) cosb[i] = 0.f;   // padding rows / columns are defined as 0
+
+  for (int o0 = 0; o0 < nt; o0 += kRowTile) {
+    const int ro = min(kRowTile, nt - o0);
+    const int ntask = (ro + 1) * npb;             // row index ro is the |k|^2 task
+    float tot[kTPW];                              // sum over template sets of cos_t
+#pragma unroll
+    for (int i = 0; i < kTPW; ++i) tot[i] = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      const float* qb = p.q + ((long long)b * p.T + t) * p.O * D + (long long)o0 * D;
+      float acc[kTPW];
+#pragma unroll
+      for (int i = 0; i < kTPW; ++i) acc[i] = 0.f;
+      float qn2 = 0.f;                            // warp w accumulates |q_w|^2 when the tile has <= 8 rows
+      for (int d0 = 0; d0 < D; d0 += kDT) {
+        const int dt = min(kDT, D - d0);
+        __syncthreads();                          // previous tile fully consumed
+        for (int i = tid; i < np * kDT; i += kThreads) {
+          const int r = i / kDT, c = i - r * kDT;
+          ks[r * kPitch + c] = c < dt ? kb[(long long)r * D + d0 + c] : 0.f;
+        }
+        for (int i = tid; i < ro * kDT; i += kThreads) {
+          const int r = i / kDT, c = i - r * kDT;
+          qs[r * kPitch + c] = c < dt ? qb[(long long)r * D + d0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kTPW; ++i) {
+          const int task = warp + kWarps * i;
+          if (task < ntask) {                     // warp-uniform
+            const int r = task / npb, pb = task - r * npb;
+            const int col = pb * 32 + lane;
+            const float* kp = ks + (col < np ? col : 0) * kPitch;
+            float a0 = 0.f, a1 = 0.f;
+            if (r < ro) {
+              const float* qp = qs + r * kPitch;
+#pragma unroll 8
+              for (int c = 0; c < kDT; c += 2) {
+                a0 = fmaf(qp[c], kp[c], a0);
+                a1 = fmaf(qp[c + 1], kp[c + 1], a1);
+              }
+            } else {
+#pragma unroll 8
+              for (int c = 0; c < kDT; c += 2) {
+                a0 = fmaf(kp[c], kp[c], a0);
+                a1 = fmaf(kp[c + 1], kp[c + 1], a1);
+              }
+            }
+            acc[i] += a0 + a1;
+          }
+        }
+        if (ro <= kWarps && warp < ro) {          // |q_r|^2 of row r = warp rides along (more than 8 rows: pass below)
+          const float* qp = qs + warp * kPitch;
+          for (int c = lane; c < kDT; c += 32) qn2 = fmaf(qp[c], qp[c], qn2);
+        }
+      }
+      // ---- norms: |q_r| per row (warps own rows r = warp, warp + 8), |k_p|^2 from the norm tasks ----------------
       __syncthreads();
-      for (int r = warp; r < ro; r += kWarps) {
-        const float* v = qb + (long long)(o0 + r) * D;
-        const float nq = fmaxf(row_norm(v, D, lane), p.eps);
-        for (int d = lane; d < D; d += 32) qs[r * D + d] = __fdiv_rn(v[d], nq);
+      if (ro <= kWarps) {
+        const float s = warp_sum(qn2);
+        if (lane == 0 && warp < ro) qnorm[warp] = fmaxf(__fsqrt_rn(s), p.eps);
+      } else {
+        for (int r = warp; r < ro; r += kWarps) {
+          const float v = row_norm(qb + (long long)r * D, D, lane);
+          if (lane == 0) qnorm[r] = fmaxf(v, p.eps);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kTPW; ++i) {
+        const int task = warp + kWarps * i;
+        if (task < ntask && task / npb == ro) {
+          const int col = (task - ro * npb) * 32 + lane;
+          if (col < np) knorm2[col] = acc[i];
+        }
       }
       __syncthreads();
-      for (int c = warp; c < np; c += kWarps) {
-        const float* kv = kb + (long long)c * D;
-        const float nk = fmaxf(row_norm(kv, D, lane), p.eps);
-        float acc[kRowTile];
 #pragma unroll
-        for (int r = 0; r < kRowTile; ++r) acc[r] = 0.f;
-        for (int d = lane; d < D; d += 32) {
-          const float kn = __fdiv_rn(kv[d], nk);
-#pragma unroll
-          for (int r = 0; r < kRowTile; ++r)
-            if (r < ro) acc[r] = fmaf(qs[r * D + d], kn, acc[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < kRowTile; ++r)
-          if (r < ro) {
-            const float s = warp_sum(acc[r]);
-            // this warp is the only writer of column c; the first template set stores (a read-modify-write here is a
-            // dependent ~0.7 us global round trip per entry: it made this kernel 60 us at B=64), later sets accumulate
-            if (lane == 0) {
-              if (t == 0) cosb[(o0 + r) * p.P + c] = s;
-              else cosb[(o0 + r) * p.P + c] += s;
-            }
+      for (int i = 0; i < kTPW; ++i) {
+        const int task = warp + kWarps * i;
+        if (task < ntask) {
+          const int r = task / npb, col = (task - r * npb) * 32 + lane;
+          if (r < ro && col < np) {
+            const float nk = fmaxf(__fsqrt_rn(knorm2[col]), p.eps);
+            tot[i] += __fdiv_rn(acc[i], __fmul_rn(qnorm[r], nk));
           }
+        }
       }
     }
-  }
-  __syncthreads();
-  if (p.T > 1) {
-    const float tf = (float)p.T;
-    for (int i = tid; i < p.O * p.P; i += kThreads) cosb[i] = __fdiv_rn(cosb[i], tf);  // feature_sim /= T
+#pragma unroll
+    for (int i = 0; i < kTPW; ++i) {
+      const int task = warp + kWarps * i;
+      if (task < ntask) {
+        const int r = task / npb, col = (task - r * npb) * 32 + lane;
+        if (r < ro && col < np) cosb[(o0 + r) * p.P + col] = p.T > 1 ? tot[i] * invT : tot[i];   // feature_sim /= T
+      }
+    }
   }
 }
 
@@ -218,10 +285,8 @@ extern "C" int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_fea
   if (B == 0 || P == 0 || O == 0) return DMM_OK;
   if (!tmpl_feat || !prop_feat || !cos) return DMM_ERR_INVALID_ARGUMENT;
   kp.cos = cos;
-  int rt = kSmemFloats / (D > 0 ? D : 1);
-  rt = rt > kRowTile ? kRowTile : (rt < 1 ? 1 : rt);
-  const size_t smem = (size_t)rt * (D > 0 ? D : 1) * sizeof(float);
-  cosine_fwd_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(kp);
+  if (P > kMaxP) return DMM_ERR_UNSUPPORTED_SHAPE;
+  cosine_fwd_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(kp);
   return check_launch();
 }
 

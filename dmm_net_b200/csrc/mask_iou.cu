@@ -29,6 +29,7 @@ static_assert(kWords == kWarps, "one bit-plane word per warp in phase B");
 
 struct IouParams {
   const float* prop;
+  const float* const* prop_ptrs;   // optional per-problem base pointers (ragged per-video tensors); overrides prop/prop_bs
   const float* tmpl;
   const float* tmpl2;
   long long prop_bs, tmpl_bs, tmpl2_bs;
@@ -76,11 +77,12 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
   const int p0 = ptile * p.PT, o0 = otile * p.OT;
   const int pcnt = min(p.PT, p.P - p0), ocnt = min(p.OT, p.Otot - o0);
   const int rows = pcnt + ocnt;
+  const float* prop_b = p.prop_ptrs ? p.prop_ptrs[b] : p.prop + (long long)b * p.prop_bs;
 
   if (tid < kMaxRows) {
     const float* ptr = nullptr;
     if (tid < pcnt) {
-      if (p0 + tid < np) ptr = p.prop + (long long)b * p.prop_bs + (long long)(p0 + tid) * p.HW;
+      if (p0 + tid < np) ptr = prop_b + (long long)(p0 + tid) * p.HW;
     } else if (tid < rows) {
       const int t = o0 + tid - pcnt;
       if (t < p.O) {
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(kThreads, 2) mask_iou_partial_kernel(const Iou
         ptr = p.tmpl2 + (long long)b * p.tmpl2_bs + (long long)(t - p.O) * p.HW;
       }
     }
-    row_ptr[tid] = ptr ? ptr : p.prop + (long long)b * p.prop_bs;  // any readable row of this problem
+    row_ptr[tid] = ptr ? ptr : p.tmpl + (long long)b * p.tmpl_bs;  // any readable row of this problem
   }
   for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kThreads) red[i] = 0;
   __syncthreads();
@@ -498,14 +500,14 @@ extern "C" size_t dmm_mask_iou_workspace_bytes(int B, int P, int O, int HW, int 
   return align_up((size_t)B * pl.S * pl.cnt * sizeof(int), 256);
 }
 
-extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, const float* tmpl,
-                                     long long tmpl_bstride, const float* tmpl2, long long tmpl2_bstride, int B,
-                                     int P, int O, int HW, const int* n_prop, const int* n_tmpl, float* iou,
-                                     float* iou2, const float* cos, float w_cos, float w_iou, float* sim,
-                                     int* counts, void* workspace, size_t workspace_bytes, void* stream) {
+static int run_pairwise(const float* prop, const float* const* prop_ptrs, int ptrs_aligned16, long long prop_bstride,
+                        const float* tmpl, long long tmpl_bstride, const float* tmpl2, long long tmpl2_bstride, int B,
+                        int P, int O, int HW, const int* n_prop, const int* n_tmpl, float* iou, float* iou2,
+                        const float* cos, float w_cos, float w_iou, float* sim, int* counts, void* workspace,
+                        size_t workspace_bytes, void* stream) {
   if (B < 0 || P < 0 || O < 0 || HW < 0) return DMM_ERR_INVALID_ARGUMENT;
   if (B == 0 || P == 0 || O == 0) return DMM_OK;  // nothing to write
-  if (!prop || !tmpl || !workspace) return DMM_ERR_INVALID_ARGUMENT;
+  if (!workspace || (HW > 0 && ((!prop && !prop_ptrs) || !tmpl))) return DMM_ERR_INVALID_ARGUMENT;
   if (sim && !cos) return DMM_ERR_INVALID_ARGUMENT;
   if (iou2 && !tmpl2) return DMM_ERR_INVALID_ARGUMENT;
   if (B > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
@@ -516,7 +518,7 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
   cudaStream_t st = (cudaStream_t)stream;
 
   IouParams kp;
-  kp.prop = prop; kp.tmpl = tmpl; kp.tmpl2 = tmpl2;
+  kp.prop = prop; kp.prop_ptrs = prop_ptrs; kp.tmpl = tmpl; kp.tmpl2 = tmpl2;
   kp.prop_bs = prop_bstride; kp.tmpl_bs = tmpl_bstride; kp.tmpl2_bs = tmpl2_bstride;
   kp.n_prop = n_prop; kp.n_tmpl = n_tmpl;
   kp.P = P; kp.O = O; kp.Otot = pl.Otot; kp.HW = HW;
@@ -528,7 +530,7 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
     DMM_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)B * pl.S * pl.cnt * sizeof(int), st));
   }
   auto aligned16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
-  const bool vec = (HW % 4 == 0) && aligned16(prop) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
+  const bool vec = (HW % 4 == 0) && (prop_ptrs ? ptrs_aligned16 != 0 : aligned16(prop)) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
                    (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
   dim3 grid(pl.S, B, pl.n_ptiles * pl.n_otiles);
   const int to = pl.OT <= 4 ? 4 : (pl.OT <= 8 ? 8 : (pl.OT <= 12 ? 12 : 16));
@@ -536,7 +538,7 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
   // measured on par with / slightly ahead of the LDG pipeline (profiles/README.md).  DMM_K1_IMPL=ldg forces the
   // LDG kernel (read-only environment lookup, used by the A/B parity test).
   const char* impl = getenv("DMM_K1_IMPL");
-  bool use_tma = vec && !(impl && impl[0] == 'l') && pl.n_ptiles == 1 && pl.n_otiles == 1 && HW >= kChunkPx;
+  bool use_tma = vec && !prop_ptrs && !(impl && impl[0] == 'l') && pl.n_ptiles == 1 && pl.n_otiles == 1 && HW >= kChunkPx;
   CUtensorMap mp, mt, mt2;
   if (use_tma) {
     use_tma = make_map(&mp, prop, prop_bstride, B, P, HW) && make_map(&mt, tmpl, tmpl_bstride, B, O, HW);
@@ -571,6 +573,25 @@ extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, 
   if (fblocks > 8 * kNumSMs) fblocks = 8 * kNumSMs;
   mask_iou_finalize_kernel<<<fblocks, 256, 0, st>>>(fp);
   return check_launch();
+}
+
+extern "C" int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, const float* tmpl,
+                                     long long tmpl_bstride, const float* tmpl2, long long tmpl2_bstride, int B,
+                                     int P, int O, int HW, const int* n_prop, const int* n_tmpl, float* iou,
+                                     float* iou2, const float* cos, float w_cos, float w_iou, float* sim,
+                                     int* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  return run_pairwise(prop, nullptr, 0, prop_bstride, tmpl, tmpl_bstride, tmpl2, tmpl2_bstride, B, P, O, HW, n_prop,
+                      n_tmpl, iou, iou2, cos, w_cos, w_iou, sim, counts, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dmm_mask_iou_pairwise_ptrs(const float* const* prop_ptrs, int ptrs_aligned16, const float* tmpl,
+                                          long long tmpl_bstride, const float* tmpl2, long long tmpl2_bstride, int B,
+                                          int P, int O, int HW, const int* n_prop, const int* n_tmpl, float* iou,
+                                          float* iou2, const float* cos, float w_cos, float w_iou, float* sim,
+                                          int* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!prop_ptrs) return DMM_ERR_INVALID_ARGUMENT;
+  return run_pairwise(nullptr, prop_ptrs, ptrs_aligned16, 0, tmpl, tmpl_bstride, tmpl2, tmpl2_bstride, B, P, O, HW,
+                      n_prop, n_tmpl, iou, iou2, cos, w_cos, w_iou, sim, counts, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t dmm_mask_iou_rowwise_workspace_bytes(int N, int M) {

@@ -3,12 +3,14 @@
 Same class name, constructor and method signatures/returns as the reference ``DMM_Model``; what changes is HOW one
 frame of a batch of videos is matched: the reference loops over videos in Python with an ``.item()`` sync per video
 (dmm_model.py:117) and three 0/1-matrix ``torch.mm`` select/scatter passes (:133-135,:156); here all videos of the
-batch go through the kernels in one launch each, valid-template counts stay on the device (``n_tmpl``), and the
-scatter of the O valid rows into the F=maxseqlen output slots is the apply kernel's ``row_map``.
+batch go through the kernels in one launch each, valid-template counts stay on the device (``n_tmpl``), the
+scatter of the O valid rows into the F=maxseqlen output slots is the apply kernel's ``row_map``, and the per-video
+proposal mask tensors are read in place through a device pointer table (no ``torch.stack`` copy).
 """
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ..utils.checker import CHECK4D, CHECKEQ
 from .feature_extractor import make_roi_mask_feature_extractor
 from .match_model import MatchModel
@@ -63,10 +65,12 @@ class DMM_Model(nn.Module):
         Pmax = max(max(boxes_per_image), 1)
         pooled = self.feature_extractor(backbone_feature, proposals).split(boxes_per_image, dim=0)
         prop_feat = _stack_pad(list(pooled), Pmax)
-        prop_mask = _stack_pad([p.get_field('mask').squeeze(1) for p in proposals], Pmax)
+        # per-video proposal masks stay where they are: the kernels read them through a device pointer table
+        prop_mask = ops.RaggedMasks([p.get_field('mask').squeeze(1) for p in proposals])
         prop_score = _stack_pad([p.get_field('objectness') if 'objectness' in p.fields() else p.get_field('scores')
                                  for p in proposals], Pmax)
         dev = prop_mask.device
+        H, W = prop_mask.shape_hw[-2:]
         valid = tplt_valid_batch.to(dev).float().view(B, -1)                            # [B,F] 0/1
         Fm = valid.shape[1]
         n_tmpl = valid.sum(1).round().to(torch.int32)                                  # stays on the device
@@ -79,15 +83,15 @@ class DMM_Model(nn.Module):
         ar = torch.arange(Fm, device=dev, dtype=torch.int32)[None, :].expand(B, -1)
         row_map = torch.where(valid > 0, ar, torch.full_like(ar, -1)).contiguous()      # scatter fused into K4
         n_prop = torch.tensor(boxes_per_image, dtype=torch.int32, device=dev)
-        return prop_feat, prop_mask, prop_score, tmpl_feat, n_prop, n_tmpl, row_map, Fm
+        return prop_feat, prop_mask, prop_score, tmpl_feat, n_prop, n_tmpl, row_map, Fm, (H, W)
 
     def _match(self, proposals, backbone_feature, mask_last_occurence, tplt_dict, tplt_valid_batch, targets, skip=None):
         B, F, H, W = CHECK4D(mask_last_occurence)
         CHECKEQ(len(proposals), B)
-        prop_feat, prop_mask, prop_score, tmpl_feat, n_prop, n_tmpl, row_map, Fm = self._gather(
+        prop_feat, prop_mask, prop_score, tmpl_feat, n_prop, n_tmpl, row_map, Fm, hw = self._gather(
             proposals, backbone_feature, tplt_dict, tplt_valid_batch, skip)
         CHECKEQ(Fm, F)
-        CHECKEQ(tuple(prop_mask.shape[-2:]), (H, W))
+        CHECKEQ(tuple(hw), (H, W))
         out = self.match_layer.forward_many(prop_feat, prop_mask, tmpl_feat, mask_last_occurence, prop_score, targets,
                                             n_prop=n_prop, n_tmpl=n_tmpl, row_map=row_map, out_rows=F)
         output_mask = out['full_outmask']                                              # [B,F,H,W], zero rows where invalid

@@ -48,6 +48,32 @@ def pad_cols(P: int, O: int) -> int:
     return max(P, O + 1)
 
 
+class RaggedMasks:
+    """Per-problem proposal mask tensors used IN PLACE through a device pointer table (no torch.stack copy):
+    tensors[b] is [P_b, H, W] (or [P_b, HW]) fp32 on the GPU; P = max P_b; n_prop[b] = P_b."""
+
+    def __init__(self, tensors):
+        assert len(tensors) > 0
+        self.tensors = [_cuda_f32(t, "prop_mask[b]") for t in tensors]       # kept alive with this object
+        t0 = self.tensors[0]
+        self.device = t0.device
+        self.shape_hw = tuple(t0.shape[1:])
+        self.HW = 1
+        for dsz in self.shape_hw:
+            self.HW *= int(dsz)
+        for t in self.tensors:
+            assert tuple(t.shape[1:]) == self.shape_hw, (t.shape, self.shape_hw)
+        self.B = len(self.tensors)
+        counts = [int(t.shape[0]) for t in self.tensors]
+        self.P = max(max(counts), 1)
+        # an empty proposal set still needs a valid address: point it at any other tensor (n_prop = 0 masks it)
+        anyptr = next((t.data_ptr() for t in self.tensors if t.numel() > 0), 0)
+        ptrs = [t.data_ptr() if t.numel() > 0 else anyptr for t in self.tensors]
+        self.aligned16 = int(all(q % 16 == 0 for q in ptrs) and self.HW % 4 == 0)
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self.n_prop = torch.tensor(counts, dtype=torch.int32, device=self.device)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # K1  mask IoU
 # ----------------------------------------------------------------------------------------------------------
@@ -56,17 +82,24 @@ def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[to
                       w_iou: float = 0.0, want_counts: bool = False):
     """prop [B,P,...], tmpl [B,O,...] (trailing dims flattened to HW) -> dict(iou [B,O,P], iou2, sim, counts)."""
     lib = _lib.load()
-    prop = _cuda_f32(prop, "prop")
+    if isinstance(prop, (list, tuple)):
+        prop = RaggedMasks(prop)
+    ragged = prop if isinstance(prop, RaggedMasks) else None
     tmpl = _cuda_f32(tmpl, "tmpl")
-    B, P = prop.shape[:2]
     O = tmpl.shape[1]
-    HW = 1
-    for dsz in prop.shape[2:]:
-        HW *= int(dsz)
-    prop = prop.reshape(B, P, HW)
-    assert tmpl.shape[0] == B and tmpl.numel() == B * O * HW, (prop.shape, tmpl.shape)
+    if ragged is not None:
+        B, P, HW = ragged.B, ragged.P, ragged.HW
+        n_prop = ragged.n_prop if n_prop is None else n_prop
+    else:
+        prop = _cuda_f32(prop, "prop")
+        B, P = prop.shape[:2]
+        HW = 1
+        for dsz in prop.shape[2:]:
+            HW *= int(dsz)
+        prop = prop.reshape(B, P, HW)
+    assert tmpl.shape[0] == B and tmpl.numel() == B * O * HW, (B, P, HW, tmpl.shape)
     tmpl = tmpl.reshape(B, O, HW)
-    dev = prop.device
+    dev = tmpl.device
     if tmpl2 is not None:
         tmpl2 = _cuda_f32(tmpl2, "tmpl2")
         assert tmpl2.numel() == tmpl.numel(), (tmpl2.shape, tmpl.shape)
@@ -90,10 +123,16 @@ def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[to
         ws_bytes = lib.dmm_mask_iou_workspace_bytes(nb, P, O, max(HW, 1), int(tmpl2 is not None))
         ws = torch.empty(max(ws_bytes, 256), device=dev, dtype=torch.uint8)
         sl = lambda t: None if t is None else t[s:e]
-        rc = lib.dmm_mask_iou_pairwise(_p(prop[s:e]), P * HW, _p(tmpl[s:e]), O * HW, _p(sl(tmpl2)), O * HW, nb, P, O, HW,
-                                       _p(sl(n_prop)), _p(sl(n_tmpl)), _p(iou[s:e]), _p(sl(iou2)), _p(sl(cos)),
-                                       float(w_cos), float(w_iou), _p(sl(sim)), _p(sl(counts)), _p(ws), ws.numel(),
-                                       _stream())
+        if ragged is not None:
+            rc = lib.dmm_mask_iou_pairwise_ptrs(_p(ragged.ptrs[s:e]), ragged.aligned16, _p(tmpl[s:e]), O * HW,
+                                                _p(sl(tmpl2)), O * HW, nb, P, O, HW, _p(sl(n_prop)), _p(sl(n_tmpl)),
+                                                _p(iou[s:e]), _p(sl(iou2)), _p(sl(cos)), float(w_cos), float(w_iou),
+                                                _p(sl(sim)), _p(sl(counts)), _p(ws), ws.numel(), _stream())
+        else:
+            rc = lib.dmm_mask_iou_pairwise(_p(prop[s:e]), P * HW, _p(tmpl[s:e]), O * HW, _p(sl(tmpl2)), O * HW, nb, P, O,
+                                           HW, _p(sl(n_prop)), _p(sl(n_tmpl)), _p(iou[s:e]), _p(sl(iou2)), _p(sl(cos)),
+                                           float(w_cos), float(w_iou), _p(sl(sim)), _p(sl(counts)), _p(ws), ws.numel(),
+                                           _stream())
         _lib.check(rc, "dmm_mask_iou_pairwise")
     return out
 
@@ -263,14 +302,62 @@ class _ApplyFn(torch.autograd.Function):
         return gB, gprop, None, None, None, None, None, None
 
 
+class _ApplyRaggedFn(torch.autograd.Function):
+    """assign_apply over a RaggedMasks pointer table (the proposal masks carry no gradient on this path)."""
+
+    @staticmethod
+    def forward(ctx, Bm, logic, n_tmpl, row_map, ragged, n_prop, O_out, zero_fill):
+        lib = _lib.load()
+        B, O, MS = Bm.shape
+        out = torch.empty(B, O_out, ragged.HW, device=Bm.device)
+        if B * O_out * ragged.HW > 0:
+            rc = lib.dmm_assign_apply_ptrs(_p(Bm), _p(ragged.ptrs), ragged.aligned16, B, ragged.P, O, MS, ragged.HW,
+                                           _p(n_prop), _p(n_tmpl), _p(row_map), O_out, int(zero_fill), _p(out),
+                                           O_out * ragged.HW, _stream())
+            _lib.check(rc, "dmm_assign_apply_ptrs")
+        ctx.save_for_backward(Bm, logic, n_tmpl, row_map, n_prop)
+        ctx.ragged = ragged
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        Bm, logic, n_tmpl, row_map, n_prop = ctx.saved_tensors
+        rg = ctx.ragged
+        B, O, MS = Bm.shape
+        g_out = g_out.contiguous().float()
+        O_out = g_out.shape[1]
+        gB = torch.zeros_like(Bm)
+        if B * O * rg.P * rg.HW > 0:
+            ws = torch.empty(lib.dmm_assign_apply_bwd_workspace_bytes(B, rg.P, O, rg.HW), device=Bm.device, dtype=torch.uint8)
+            sel = logic if logic is not None else (Bm != 0).float()
+            rc = lib.dmm_assign_apply_bwd_ptrs(_p(g_out), O_out * rg.HW, _p(rg.ptrs), rg.aligned16, _p(Bm), _p(sel), B, rg.P,
+                                               O, MS, rg.HW, _p(n_prop), _p(n_tmpl), _p(row_map), _p(gB), _p(ws), ws.numel(),
+                                               _stream())
+            _lib.check(rc, "dmm_assign_apply_bwd_ptrs")
+        return gB, None, None, None, None, None, None, None
+
+
 def assign_apply(Bm: torch.Tensor, prop: torch.Tensor, logic: Optional[torch.Tensor] = None, n_prop=None, n_tmpl=None,
                  row_map: Optional[torch.Tensor] = None, O_out: Optional[int] = None, zero_fill: bool = True):
     """Bmat [B,O,MS] x prop [B,P,HW] -> out [B,O_out,HW]; row o of problem b lands in row row_map[b,o].
     ``logic`` (the solver's selection mask) restricts the gradient w.r.t. Bmat to the selected entries, exactly the
     entries through which the reference's ``R * logic_mask`` lets gradient flow."""
     Bm = _cuda_f32(Bm, "Bmat")
-    prop = _cuda_f32(prop, "prop")
     B, O, MS = Bm.shape
+    if isinstance(prop, (list, tuple)):
+        prop = RaggedMasks(prop)
+    if isinstance(prop, RaggedMasks):
+        dev = Bm.device
+        if row_map is not None:
+            row_map = torch.as_tensor(row_map, device=dev).to(torch.int32).contiguous()
+            assert row_map.shape == (B, O)
+        if logic is not None:
+            logic = _cuda_f32(logic, "logic")
+        n_prop = prop.n_prop if n_prop is None else _counts(n_prop, B, dev)
+        return _ApplyRaggedFn.apply(Bm, logic, _counts(n_tmpl, B, dev), row_map, prop, n_prop,
+                                    int(O if O_out is None else O_out), bool(zero_fill))
+    prop = _cuda_f32(prop, "prop")
     prop = prop.reshape(B, prop.shape[1], -1)
     dev = prop.device
     if row_map is not None:
@@ -349,10 +436,17 @@ def match_batch(prop_feat: torch.Tensor, prop_mask: torch.Tensor, tmpl_feat: tor
     """
     if tmpl_feat.dim() == 3:
         tmpl_feat = tmpl_feat.unsqueeze(1)
-    B, P = prop_mask.shape[:2]
+    if isinstance(prop_mask, (list, tuple)):
+        prop_mask = RaggedMasks(prop_mask)                      # per-video tensors used in place (pointer table)
+    if isinstance(prop_mask, RaggedMasks):
+        B, P = prop_mask.B, prop_mask.P
+        n_prop = prop_mask.n_prop if n_prop is None else n_prop
+        assert prop_feat.shape[1] == P and prop_score.shape[1] == P, "features / scores must be padded to max P_b"
+    else:
+        B, P = prop_mask.shape[:2]
     O = tmpl_mask.shape[1]
-    H, W = prop_mask.shape[-2:]
-    dev = prop_mask.device
+    H, W = tmpl_mask.shape[-2:]
+    dev = tmpl_mask.device
     n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
     cos = cosine_pairwise(tmpl_feat, prop_feat, n_prop, n_tmpl)                       # K2
     w = float(score_weight)

@@ -62,6 +62,15 @@ int dmm_mask_iou_pairwise(const float* prop, long long prop_bstride, const float
                           float w_cos, float w_iou, float* sim, int* counts, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Same, with the proposals of problem b at prop_ptrs[b] (device array of B device pointers, each [n_prop[b] or P][HW]):
+ * the per-video proposal tensors of dmm_model.py:111 are used in place, without the torch.stack copy (23 MB per video
+ * and frame at the headline size).  ptrs_aligned16 != 0 promises that every pointer is 16-byte aligned. */
+int dmm_mask_iou_pairwise_ptrs(const float* const* prop_ptrs, int ptrs_aligned16, const float* tmpl,
+                               long long tmpl_bstride, const float* tmpl2, long long tmpl2_bstride, int B, int P, int O,
+                               int HW, const int* n_prop, const int* n_tmpl, float* iou, float* iou2, const float* cos,
+                               float w_cos, float w_iou, float* sim, int* counts, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* Row-paired IoU: a[N][M] vs b[N][M] -> iou[N]  (compute_iou_binary_mask_2D itself; callers trainer.py:190,298). */
 size_t dmm_mask_iou_rowwise_workspace_bytes(int N, int M);
 int dmm_mask_iou_rowwise(const float* a, const float* b, int N, int M, float* iou, void* workspace,
@@ -85,7 +94,7 @@ int dmm_cosine_pairwise_bwd(const float* g_cos, const float* tmpl_feat, const fl
  * match_with_first_frame (match_model.py:109-130,146-147): zero-column padding when P<=O, C=-sim,
  * R = mean of the PRE-projection iterates, logic = (R==rowmax) [is_test] or (R>0.01), Bmat = R*logic,
  * match_score = max_p(clamp(R,0,1)*sim), det_score = sum_p score_p*Bmat.
- * One warp per problem; X, the three Dykstra increments, C and the running sum of iterates stay in registers.
+ * One CTA of 4 warps per problem; X, the three Dykstra increments, C and the running sum of iterates stay in registers.
  *
  * in : mat [B][O][P]  (a similarity if negate!=0, else used as the cost C directly), prop_score [B][P] or NULL
  * out: (any may be NULL)  R, X_final, Bmat, logic [B][O][MS];  match_score, det_score [B][O];
@@ -119,6 +128,9 @@ int dmm_relax_solve_bwd(const float* g_R, const float* g_Xfinal, const float* g_
 int dmm_assign_apply(const float* Bmat, const float* prop, long long prop_bstride, int B, int P, int O, int MS,
                      int HW, const int* n_prop, const int* n_tmpl, const int* row_map, int O_out, int zero_fill,
                      float* out, long long out_bstride, void* stream);
+int dmm_assign_apply_ptrs(const float* Bmat, const float* const* prop_ptrs, int ptrs_aligned16, int B, int P, int O,
+                          int MS, int HW, const int* n_prop, const int* n_tmpl, const int* row_map, int O_out,
+                          int zero_fill, float* out, long long out_bstride, void* stream);
 /* g_Bmat[b,o,p] = <g_out[b,row(o),:], prop[b,p,:]> for the entries selected by `logic` (others 0);
  * optional g_prop [B][P][HW] = Bmat^T g_out (overwritten) when the proposal masks need a gradient. */
 size_t dmm_assign_apply_bwd_workspace_bytes(int B, int P, int O, int HW);
@@ -126,6 +138,11 @@ int dmm_assign_apply_bwd(const float* g_out, long long gout_bstride, const float
                          const float* Bmat, const float* logic, int B, int P, int O, int MS, int HW,
                          const int* n_prop, const int* n_tmpl, const int* row_map, float* g_Bmat, float* g_prop,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+int dmm_assign_apply_bwd_ptrs(const float* g_out, long long gout_bstride, const float* const* prop_ptrs,
+                              int ptrs_aligned16, const float* Bmat, const float* logic, int B, int P, int O, int MS,
+                              int HW, const int* n_prop, const int* n_tmpl, const int* row_map, float* g_Bmat,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K5: ROI mean pooling -----------------------------------------------------------------------------
  * Replaces FeatureExtractor.forward (feature_extractor.py:20-52): legacy ROIAlign(14x14, sampling_ratio 2,

@@ -112,3 +112,28 @@ def test_batched_container_equals_per_video_loop(is_test):
             np.testing.assert_allclose(float(loss[b]), float(want_loss[b]), rtol=0, atol=1e-5)
     np.testing.assert_allclose(out.detach().cpu().numpy(), want_out.numpy(), rtol=0, atol=1e-4)
     np.testing.assert_allclose(last.detach().cpu().numpy(), want_last.numpy(), rtol=0, atol=1e-4)
+
+
+def test_ragged_pointer_table_equals_stacked_batch():
+    """Per-video proposal tensors through the device pointer table == the padded [B,P,H,W] batch (K1 and K4)."""
+    B, P, O, H, W, D = 4, 14, 3, 40, 52, 32
+    pr = make_problems(B, P, O, H, W, D, seed=77).to(DEV)
+    counts = [14, 9, 1, 6]
+    plist = [pr.prop_mask[b, :n].clone() for b, n in enumerate(counts)]          # separate allocations
+    n_prop = torch.tensor(counts, device=DEV, dtype=torch.int32)
+    a = ops.mask_iou_pairwise(pr.prop_mask, pr.tmpl_mask, n_prop=n_prop)["iou"]
+    b_ = ops.mask_iou_pairwise(plist, pr.tmpl_mask)["iou"]
+    assert torch.equal(a, b_)
+    kw = dict(max_iter=20, proj_iter=5, lr=0.1, score_weight=0.3, is_test=True)
+    with torch.no_grad():
+        ref = ops.match_batch(pr.prop_feat, pr.prop_mask, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score, n_prop=n_prop, **kw)
+        got = ops.match_batch(pr.prop_feat, plist, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score, **kw)
+    for k in ("full_outmask", "match_score", "det_score", "R"):
+        assert torch.equal(ref[k], got[k]), k
+    # training direction: gradient w.r.t. the assignment through the pointer-table backward
+    Bm = ref["Bmat"].clone().requires_grad_(True)
+    Bm2 = ref["Bmat"].clone().requires_grad_(True)
+    w = torch.rand(B, O, H * W, device=DEV)
+    (ops.assign_apply(Bm, pr.prop_mask, ref["logic"], n_prop=n_prop) * w).sum().backward()
+    (ops.assign_apply(Bm2, plist, ref["logic"]) * w).sum().backward()
+    assert torch.allclose(Bm.grad, Bm2.grad, rtol=1e-5, atol=1e-5)
