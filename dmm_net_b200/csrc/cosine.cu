@@ -47,11 +47,22 @@ constexpr int kMaxP = 128;              // proposals per problem (solver limit)
 constexpr int kMaxTasks = (kRowTile + 1) * (kMaxP / 32);   // 68
 constexpr int kTPW = (kMaxTasks + kWarps - 1) / kWarps;    // 9 accumulators per lane at most
 
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;   // src-size 0 zero-fills the destination
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr size_t kCosSmem = (size_t)2 * (kMaxP + kRowTile) * kPitch * sizeof(float);   // double-buffered tiles: 74.9 KB
+
 __global__ void __launch_bounds__(kThreads) cosine_fwd_kernel(const CosParams p) {
-  __shared__ float ks[kMaxP * kPitch];            // proposal feature tile   [np][kDT]
-  __shared__ float qs[kRowTile * kPitch];         // template feature tile   [ro][kDT]
+  extern __shared__ float tile[];                 // [2][ (kMaxP + kRowTile) * kPitch ]: proposals then templates
   __shared__ float knorm2[kMaxP];
   __shared__ float qnorm[kRowTile];
+  constexpr int kBuf = (kMaxP + kRowTile) * kPitch;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
   const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
@@ -60,6 +71,7 @@ __global__ void __launch_bounds__(kThreads) cosine_fwd_kernel(const CosParams p)
   const float* kb = p.k + (long long)b * p.P * D;
   const int npb = (np + 31) / 32;                 // proposal blocks of 32 lanes
   const float invT = 1.f / (float)p.T;
+  const int ntiles = (D + kDT - 1) / kDT;
   for (int i = tid; i < p.O * p.P; i += kThreads) cosb[i] = 0.f;   // padding rows / columns are defined as 0
 
   for (int o0 = 0; o0 < nt; o0 += kRowTile) {
@@ -70,22 +82,33 @@ __global__ void __launch_bounds__(kThreads) cosine_fwd_kernel(const CosParams p)
     for (int i = 0; i < kTPW; ++i) tot[i] = 0.f;
     for (int t = 0; t < p.T; ++t) {
       const float* qb = p.q + ((long long)b * p.T + t) * p.O * D + (long long)o0 * D;
+      // cp.async stage of feature columns [d0, d0+kDT) into buffer `buf` (zero-filled past D)
+      auto stage_tile = [&](int ti, int buf) {
+        float* ks = tile + buf * kBuf;
+        float* qs = ks + kMaxP * kPitch;
+        const int d0 = ti * kDT, dt = min(kDT, D - d0);
+        for (int i = tid; i < np * kDT; i += kThreads) {
+          const int r = i / kDT, c = i - r * kDT;
+          cp_async_f32(ks + r * kPitch + c, kb + (long long)r * D + d0 + (c < dt ? c : 0), c < dt);
+        }
+        for (int i = tid; i < ro * kDT; i += kThreads) {
+          const int r = i / kDT, c = i - r * kDT;
+          cp_async_f32(qs + r * kPitch + c, qb + (long long)r * D + d0 + (c < dt ? c : 0), c < dt);
+        }
+        cp_async_commit();
+      };
       float acc[kTPW];
 #pragma unroll
       for (int i = 0; i < kTPW; ++i) acc[i] = 0.f;
       float qn2 = 0.f;                            // warp w accumulates |q_w|^2 when the tile has <= 8 rows
-      for (int d0 = 0; d0 < D; d0 += kDT) {
-        const int dt = min(kDT, D - d0);
-        __syncthreads();                          // previous tile fully consumed
-        for (int i = tid; i < np * kDT; i += kThreads) {
-          const int r = i / kDT, c = i - r * kDT;
-          ks[r * kPitch + c] = c < dt ? kb[(long long)r * D + d0 + c] : 0.f;
-        }
-        for (int i = tid; i < ro * kDT; i += kThreads) {
-          const int r = i / kDT, c = i - r * kDT;
-          qs[r * kPitch + c] = c < dt ? qb[(long long)r * D + d0 + c] : 0.f;
-        }
-        __syncthreads();
+      __syncthreads();                            // buffers free (previous template set / row tile done)
+      if (ntiles > 0) stage_tile(0, 0);
+      for (int ti = 0; ti < ntiles; ++ti) {
+        const int buf = ti & 1;
+        if (ti + 1 < ntiles) { stage_tile(ti + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();                          // tile ti landed for every thread
+        const float* ks = tile + buf * kBuf;
+        const float* qs = ks + kMaxP * kPitch;
 #pragma unroll
         for (int i = 0; i < kTPW; ++i) {
           const int task = warp + kWarps * i;
@@ -115,9 +138,9 @@ __global__ void __launch_bounds__(kThreads) cosine_fwd_kernel(const CosParams p)
           const float* qp = qs + warp * kPitch;
           for (int c = lane; c < kDT; c += 32) qn2 = fmaf(qp[c], qp[c], qn2);
         }
+        __syncthreads();                          // tile ti consumed: its buffer may be refilled by stage_tile(ti + 2)
       }
       // ---- norms: |q_r| per row (warps own rows r = warp, warp + 8), |k_p|^2 from the norm tasks ----------------
-      __syncthreads();
       if (ro <= kWarps) {
         const float s = warp_sum(qn2);
         if (lane == 0 && warp < ro) qnorm[warp] = fmaxf(__fsqrt_rn(s), p.eps);
@@ -286,7 +309,8 @@ extern "C" int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_fea
   if (!tmpl_feat || !prop_feat || !cos) return DMM_ERR_INVALID_ARGUMENT;
   kp.cos = cos;
   if (P > kMaxP) return DMM_ERR_UNSUPPORTED_SHAPE;
-  cosine_fwd_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(kp);
+  DMM_CUDA_TRY(cudaFuncSetAttribute(cosine_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCosSmem));
+  cosine_fwd_kernel<<<B, kThreads, kCosSmem, (cudaStream_t)stream>>>(kp);
   return check_launch();
 }
 
