@@ -26,6 +26,7 @@ struct CosParams {
   float eps;
   float* cos;       // [B][O][P]
   const float* g;   // bwd: [B][O][P]
+  const float* cos_fwd;  // bwd, optional: the forward's output (valid as cos_t only when T == 1)
   float* gq;        // bwd: [B][T][O][D]
   float* gk;        // bwd: [B][P][D]
 };
@@ -227,15 +228,24 @@ __global__ void __launch_bounds__(kThreads) cosine_bwd_kernel(const CosParams p)
         w[r * P + c] = c < np ? gb[(o0 + r) * P + c] * invT : 0.f;
       }
       __syncthreads();
-      // phase 1: cos_t of the tile (one warp per (row, proposal) pair)
-      for (int i = warp; i < ro * np; i += kWarps) {
-        const int r = i / np, c = i - r * np;
-        const float* qv = qb + (long long)(o0 + r) * D;
-        const float* kv = kb + (long long)c * D;
-        float s = 0.f;
-        for (int d = lane; d < D; d += 32) s = fmaf(qv[d] / nq[r], kv[d] / nk[c], s);
-        s = warp_sum(s);
-        if (lane == 0) ct[r * P + c] = s;
+      // phase 1: cos_t of the tile -- the forward's output when there is one template set (the only case the reference
+      // ever runs, dmm_model.py:44), else recomputed (one warp per (row, proposal) pair)
+      if (p.cos_fwd != nullptr && p.T == 1) {
+        const float* cf = p.cos_fwd + (long long)b * p.O * P;
+        for (int i = tid; i < ro * np; i += kThreads) {
+          const int r = i / np, c = i - r * np;
+          ct[r * P + c] = cf[(o0 + r) * P + c];
+        }
+      } else {
+        for (int i = warp; i < ro * np; i += kWarps) {
+          const int r = i / np, c = i - r * np;
+          const float* qv = qb + (long long)(o0 + r) * D;
+          const float* kv = kb + (long long)c * D;
+          float s = 0.f;
+          for (int d = lane; d < D; d += 32) s = fmaf(qv[d] / nq[r], kv[d] / nk[c], s);
+          s = warp_sum(s);
+          if (lane == 0) ct[r * P + c] = s;
+        }
       }
       __syncthreads();
       for (int r = warp; r < ro; r += kWarps) {  // sq[r] = sum_p w*cos
@@ -259,8 +269,10 @@ __global__ void __launch_bounds__(kThreads) cosine_bwd_kernel(const CosParams p)
           qh[r] = r < ro ? qb[(long long)(o0 + r) * D + d] / nq[r] : 0.f;
           A[r] = 0.f;
         }
+        const bool first = (t == 0 && o0 == 0);   // first tile stores, later tiles accumulate (no RMW round trips)
+#pragma unroll 4
         for (int c = 0; c < np; ++c) {
-          const float kraw = kb[(long long)c * D + d];
+          const float kraw = __ldg(kb + (long long)c * D + d);
           const float kh = kraw / nk[c];
           float bq = 0.f;
 #pragma unroll
@@ -271,7 +283,9 @@ __global__ void __launch_bounds__(kThreads) cosine_bwd_kernel(const CosParams p)
               bq = fmaf(wv, qh[r], bq);
             }
           const float unit = rk[c] > 0.f ? kraw / rk[c] : 0.f;
-          gkb[(long long)c * D + d] += (bq - sk[c] * unit) / nk[c];
+          const float gval = (bq - sk[c] * unit) / nk[c];
+          if (first) gkb[(long long)c * D + d] = gval;
+          else gkb[(long long)c * D + d] += gval;
         }
 #pragma unroll
         for (int r = 0; r < kRowTile; ++r)
@@ -296,7 +310,7 @@ static int fill_params(CosParams& kp, const float* q, const float* k, int B, int
   if (D > kSmemFloats) return DMM_ERR_UNSUPPORTED_SHAPE;
   kp.q = q; kp.k = k; kp.B = B; kp.T = T; kp.P = P; kp.O = O; kp.D = D;
   kp.n_prop = n_prop; kp.n_tmpl = n_tmpl; kp.eps = eps;
-  kp.cos = nullptr; kp.g = nullptr; kp.gq = nullptr; kp.gk = nullptr;
+  kp.cos = nullptr; kp.g = nullptr; kp.cos_fwd = nullptr; kp.gq = nullptr; kp.gk = nullptr;
   return DMM_OK;
 }
 
@@ -314,15 +328,16 @@ extern "C" int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_fea
   return check_launch();
 }
 
-extern "C" int dmm_cosine_pairwise_bwd(const float* g_cos, const float* tmpl_feat, const float* prop_feat, int B,
-                                       int T, int P, int O, int D, const int* n_prop, const int* n_tmpl, float eps,
-                                       float* g_tmpl_feat, float* g_prop_feat, void* stream) {
+extern "C" int dmm_cosine_pairwise_bwd(const float* g_cos, const float* cos_fwd, const float* tmpl_feat,
+                                       const float* prop_feat, int B, int T, int P, int O, int D, const int* n_prop,
+                                       const int* n_tmpl, float eps, float* g_tmpl_feat, float* g_prop_feat,
+                                       void* stream) {
   CosParams kp;
   int rc = fill_params(kp, tmpl_feat, prop_feat, B, T, P, O, D, n_prop, n_tmpl, eps);
   if (rc) return rc;
   if (B == 0 || P == 0 || O == 0 || D == 0) return DMM_OK;
   if (!g_cos || !tmpl_feat || !prop_feat || !g_tmpl_feat || !g_prop_feat) return DMM_ERR_INVALID_ARGUMENT;
-  kp.g = g_cos; kp.gq = g_tmpl_feat; kp.gk = g_prop_feat;
+  kp.g = g_cos; kp.cos_fwd = cos_fwd; kp.gq = g_tmpl_feat; kp.gk = g_prop_feat;
   const size_t smem = ((size_t)2 * kRowTile * P + 3 * P + 3 * kRowTile) * sizeof(float);
   if (smem > 48 * 1024) return DMM_ERR_UNSUPPORTED_SHAPE;
   cosine_bwd_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(kp);

@@ -59,9 +59,13 @@ __device__ __forceinline__ void axis_range(float lo, float hi, int size, float s
   b = clampi((int)floorf(t1) + 1, 0, size - 1);
 }
 
-template <bool BWD>
+// TABLE = true: the ROI window is flattened into a shared-memory table of (element offset, wy*wx) pairs built once
+// per (ROI, level) and reused by all channels: lanes walk the window linearly (full lane utilisation even for the
+// 3..8 pixel wide windows of the coarse levels, where a lane-per-column loop idles 75-90 % of the warp).
+// TABLE = false: same arithmetic with on-the-fly index math, for feature maps too large for the table.
+template <bool BWD, bool TABLE>
 __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParams p) {
-  extern __shared__ float wsm[];  // wy[H] wx[W]
+  extern __shared__ float wsm[];  // wy[H] wx[W] | table: off[hh*ww] (int), w[hh*ww] (float)
   const int r = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H[l], W = p.W[l];
   const float scale = 0.25f / (float)(1 << l);  // 1/4, 1/8, 1/16, 1/32 (feature_extractor.py:13)
@@ -75,7 +79,18 @@ __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParam
   int ya, yb, xa, xb;
   axis_range(y1, y2, H, scale, ya, yb);
   axis_range(x1, x2, W, scale, xa, xb);
+  const int ww = xb - xa + 1, hh = yb - ya + 1, cnt = ww * hh;
+  int* toff = reinterpret_cast<int*>(wsm + H + W);
+  float* tw = wsm + H + W + (TABLE ? H * W : 0);
   __syncthreads();
+  if (TABLE) {
+    for (int i = tid; i < cnt; i += kThreads) {
+      const int y = ya + i / ww, x = xa + i % ww;
+      toff[i] = y * W + x;
+      tw[i] = wy[y] * wx[x];
+    }
+    __syncthreads();
+  }
   const bool valid = n >= 0 && n < p.N;
   if (!BWD) {
     float* o = p.out + (long long)r * 4 * p.C + (long long)l * p.C;
@@ -83,12 +98,23 @@ __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParam
       float acc = 0.f;
       if (valid) {
         const float* f = p.feat[l] + ((long long)n * p.C + c) * H * W;
-        for (int y = ya; y <= yb; ++y) {
-          const float wyv = wy[y];
-          if (wyv == 0.f) continue;
-          float rowacc = 0.f;
-          for (int x = xa + lane; x <= xb; x += 32) rowacc = fmaf(wx[x], f[y * W + x], rowacc);
-          acc = fmaf(wyv, rowacc, acc);
+        if (TABLE) {
+          float a0 = 0.f, a1 = 0.f;
+          int i = lane;
+          for (; i + 32 < cnt; i += 64) {
+            a0 = fmaf(tw[i], __ldg(f + toff[i]), a0);
+            a1 = fmaf(tw[i + 32], __ldg(f + toff[i + 32]), a1);
+          }
+          if (i < cnt) a0 = fmaf(tw[i], __ldg(f + toff[i]), a0);
+          acc = a0 + a1;
+        } else {
+          for (int y = ya; y <= yb; ++y) {
+            const float wyv = wy[y];
+            if (wyv == 0.f) continue;
+            float rowacc = 0.f;
+            for (int x = xa + lane; x <= xb; x += 32) rowacc = fmaf(wx[x], f[y * W + x], rowacc);
+            acc = fmaf(wyv, rowacc, acc);
+          }
         }
       }
       acc = warp_sum(acc);
@@ -97,15 +123,16 @@ __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParam
   } else {
     if (!valid) return;
     const float* go = p.gout + (long long)r * 4 * p.C + (long long)l * p.C;
-    const int ww = xb - xa + 1, hh = yb - ya + 1;
     for (int c = warp; c < p.C; c += kWarps) {
       const float g = go[c];
       if (g == 0.f) continue;
       float* f = p.gfeat[l] + ((long long)n * p.C + c) * H * W;
-      for (int i = lane; i < ww * hh; i += 32) {
-        const int y = ya + i / ww, x = xa + i % ww;
-        const float wgt = wy[y] * wx[x];
-        if (wgt != 0.f) atomicAdd(f + y * W + x, g * wgt);
+      for (int i = lane; i < cnt; i += 32) {
+        int off;
+        float wgt;
+        if (TABLE) { off = toff[i]; wgt = tw[i]; }
+        else { const int y = ya + i / ww, x = xa + i % ww; off = y * W + x; wgt = wy[y] * wx[x]; }
+        if (wgt != 0.f) atomicAdd(f + off, g * wgt);
       }
     }
   }
@@ -116,7 +143,8 @@ __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParam
 
 using namespace dmm;
 
-static int fill(PoolParams& kp, const int Hl[4], const int Wl[4], int N, int C, const float* rois, int R, size_t& smem) {
+static int fill(PoolParams& kp, const int Hl[4], const int Wl[4], int N, int C, const float* rois, int R, size_t& smem,
+                size_t& table_smem) {
   if (N < 0 || C < 0 || R < 0 || !Hl || !Wl) return DMM_ERR_INVALID_ARGUMENT;
   smem = 0;
   for (int l = 0; l < 4; ++l) {
@@ -127,32 +155,48 @@ static int fill(PoolParams& kp, const int Hl[4], const int Wl[4], int N, int C, 
     kp.feat[l] = nullptr; kp.gfeat[l] = nullptr;
   }
   if (smem > 48 * 1024) return DMM_ERR_UNSUPPORTED_SHAPE;
+  size_t tab = 0;
+  for (int l = 0; l < 4; ++l) {
+    const size_t need = (size_t)(Hl[l] + Wl[l]) * sizeof(float) + (size_t)Hl[l] * Wl[l] * 8;
+    if (need > tab) tab = need;
+  }
+  table_smem = tab <= 200 * 1024 ? tab : 0;   // 0: feature maps too large for the window table -> index math path
   kp.N = N; kp.C = C; kp.R = R; kp.rois = rois; kp.out = nullptr; kp.gout = nullptr;
   return DMM_OK;
 }
 
 extern "C" int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], const int Wl[4], int N, int C,
                                  const float* rois, int R, float* out, void* stream) {
-  PoolParams kp; size_t smem;
-  int rc = fill(kp, Hl, Wl, N, C, rois, R, smem);
+  PoolParams kp; size_t smem, tsmem;
+  int rc = fill(kp, Hl, Wl, N, C, rois, R, smem, tsmem);
   if (rc) return rc;
   if (R == 0 || C == 0) return DMM_OK;
   if (!feat || !rois || !out) return DMM_ERR_INVALID_ARGUMENT;
   for (int l = 0; l < 4; ++l) { if (!feat[l]) return DMM_ERR_INVALID_ARGUMENT; kp.feat[l] = feat[l]; }
   kp.out = out;
-  roi_mean_pool_kernel<false><<<dim3(R, 4), kThreads, smem, (cudaStream_t)stream>>>(kp);
+  if (tsmem) {
+    DMM_CUDA_TRY(cudaFuncSetAttribute(roi_mean_pool_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    roi_mean_pool_kernel<false, true><<<dim3(R, 4), kThreads, tsmem, (cudaStream_t)stream>>>(kp);
+  } else {
+    roi_mean_pool_kernel<false, false><<<dim3(R, 4), kThreads, smem, (cudaStream_t)stream>>>(kp);
+  }
   return check_launch();
 }
 
 extern "C" int dmm_roi_mean_pool_bwd(const float* g_out, const int Hl[4], const int Wl[4], int N, int C,
                                      const float* rois, int R, float* const g_feat[4], void* stream) {
-  PoolParams kp; size_t smem;
-  int rc = fill(kp, Hl, Wl, N, C, rois, R, smem);
+  PoolParams kp; size_t smem, tsmem;
+  int rc = fill(kp, Hl, Wl, N, C, rois, R, smem, tsmem);
   if (rc) return rc;
   if (R == 0 || C == 0) return DMM_OK;
   if (!g_feat || !rois || !g_out) return DMM_ERR_INVALID_ARGUMENT;
   for (int l = 0; l < 4; ++l) { if (!g_feat[l]) return DMM_ERR_INVALID_ARGUMENT; kp.gfeat[l] = g_feat[l]; }
   kp.gout = g_out;
-  roi_mean_pool_kernel<true><<<dim3(R, 4), kThreads, smem, (cudaStream_t)stream>>>(kp);
+  if (tsmem) {
+    DMM_CUDA_TRY(cudaFuncSetAttribute(roi_mean_pool_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    roi_mean_pool_kernel<true, true><<<dim3(R, 4), kThreads, tsmem, (cudaStream_t)stream>>>(kp);
+  } else {
+    roi_mean_pool_kernel<true, false><<<dim3(R, 4), kThreads, smem, (cudaStream_t)stream>>>(kp);
+  }
   return check_launch();
 }

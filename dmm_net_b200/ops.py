@@ -116,6 +116,14 @@ def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[to
     out = {"iou": iou, "iou2": iou2, "sim": sim, "counts": counts}
     if B == 0 or P == 0 or O == 0:
         return out
+    if tmpl2 is not None and (P + 2 * O > 64 or 2 * O > 16) and P + O <= 64 and O <= 16:
+        # both template sets in one pass would need several tiles (rows re-read, LDG path); two single-tile passes
+        # keep the TMA ring and read the proposals twice instead of up to four times
+        first = mask_iou_pairwise(ragged if ragged is not None else prop, tmpl, None, n_prop, n_tmpl, cos, w_cos, w_iou,
+                                  want_counts)
+        second = mask_iou_pairwise(ragged if ragged is not None else prop, tmpl2, None, n_prop, n_tmpl)
+        first["iou2"] = second["iou"]
+        return first
     step = 65535  # grid.y limit
     for s in range(0, B, step):
         e = min(B, s + step)
@@ -167,21 +175,21 @@ class _CosineFn(torch.autograd.Function):
             rc = lib.dmm_cosine_pairwise(_p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop), _p(n_tmpl),
                                          float(eps), _p(cos), _stream())
             _lib.check(rc, "dmm_cosine_pairwise")
-        ctx.save_for_backward(tmpl_feat, prop_feat, n_prop, n_tmpl)
+        ctx.save_for_backward(tmpl_feat, prop_feat, n_prop, n_tmpl, cos)
         ctx.eps = eps
         return cos
 
     @staticmethod
     def backward(ctx, g_cos):
         lib = _lib.load()
-        tmpl_feat, prop_feat, n_prop, n_tmpl = ctx.saved_tensors
+        tmpl_feat, prop_feat, n_prop, n_tmpl, cos = ctx.saved_tensors
         B, T, O, D = tmpl_feat.shape
         P = prop_feat.shape[1]
         g_cos = g_cos.contiguous().float()
         gq = torch.zeros_like(tmpl_feat)
         gk = torch.zeros_like(prop_feat)
         if B * O * P * D > 0:
-            rc = lib.dmm_cosine_pairwise_bwd(_p(g_cos), _p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop),
+            rc = lib.dmm_cosine_pairwise_bwd(_p(g_cos), _p(cos), _p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop),
                                              _p(n_tmpl), float(ctx.eps), _p(gq), _p(gk), _stream())
             _lib.check(rc, "dmm_cosine_pairwise_bwd")
         return gq, gk, None, None, None

@@ -83,9 +83,10 @@ int dmm_mask_iou_rowwise(const float* a, const float* b, int N, int M, float* io
  */
 int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
                         const int* n_prop, const int* n_tmpl, float eps, float* cos, void* stream);
-/* d(loss)/d(features) from g_cos [B][O][P]; g_tmpl_feat [B][T][O][D], g_prop_feat [B][P][D] are overwritten. */
-int dmm_cosine_pairwise_bwd(const float* g_cos, const float* tmpl_feat, const float* prop_feat, int B, int T,
-                            int P, int O, int D, const int* n_prop, const int* n_tmpl, float eps,
+/* d(loss)/d(features) from g_cos [B][O][P]; g_tmpl_feat [B][T][O][D], g_prop_feat [B][P][D] are overwritten.
+ * cos_fwd (optional, may be NULL): the forward's output; used instead of recomputing the cosines when T == 1. */
+int dmm_cosine_pairwise_bwd(const float* g_cos, const float* cos_fwd, const float* tmpl_feat, const float* prop_feat,
+                            int B, int T, int P, int O, int D, const int* n_prop, const int* n_tmpl, float eps,
                             float* g_tmpl_feat, float* g_prop_feat, void* stream);
 
 /* ---- K3: relaxed matching solver + assignment head ----------------------------------------------------
