@@ -432,6 +432,113 @@ def roi_mean_pool(features: Sequence[torch.Tensor], rois: torch.Tensor) -> torch
 # ----------------------------------------------------------------------------------------------------------
 # the fused layer over a batch of problems
 # ----------------------------------------------------------------------------------------------------------
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev: torch.device):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return _SIDE_STREAMS[key]
+
+
+def cost_and_solve(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, max_iter: int, proj_iter: int, lr: float,
+                   score_weight: float, is_test: bool, n_prop=None, n_tmpl=None, chunks: Optional[int] = None,
+                   k1_events: Optional[list] = None):
+    """Inference path (no autograd) of cost-build + solve for a dense batch: K2 -> K1(+finalize/mix) -> K3.
+
+    Large batches are cut into chunks that run on two side streams, staggered so that the HBM-bound K1 launches stay
+    back to back while the latency-bound cosine of the next chunk and the solver of the previous chunk run underneath
+    them (the TMA K1 kernel leaves registers and shared memory for one solver CTA per SM).  Every output is allocated
+    on the caller's stream, which waits for both side streams before returning, so results and memory lifetimes are
+    exactly those of the single-stream order; ``DMM_PIPELINE=0`` or ``chunks=1`` disables the overlap.
+    ``k1_events``: optional list that receives one (start, end) CUDA-event pair per K1 launch, recorded on the stream
+    the kernel runs on (bench.py's roofline timing).
+    Returns dict(sim, cos, iou, R, Bmat, logic, X_final, match_score, det_score, n_list)."""
+    import os
+    lib = _lib.load()
+    if tmpl_feat.dim() == 3:
+        tmpl_feat = tmpl_feat.unsqueeze(1)
+    prop_feat, tmpl_feat = _cuda_f32(prop_feat, "prop_feat"), _cuda_f32(tmpl_feat, "tmpl_feat")
+    prop_mask, tmpl_mask = _cuda_f32(prop_mask, "prop_mask"), _cuda_f32(tmpl_mask, "tmpl_mask")
+    prop_score = _cuda_f32(prop_score, "prop_score")
+    B, P = prop_mask.shape[:2]
+    O = tmpl_mask.shape[1]
+    T, D = tmpl_feat.shape[1], tmpl_feat.shape[3]
+    HW = 1
+    for dsz in prop_mask.shape[2:]:
+        HW *= int(dsz)
+    dev = prop_mask.device
+    MS = pad_cols(P, O)
+    n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
+    w = float(score_weight)
+    new = lambda *shape: torch.empty(*shape, device=dev)
+    out = {"cos": new(B, O, P), "iou": new(B, O, P), "sim": new(B, O, P), "R": new(B, O, MS), "Bmat": new(B, O, MS),
+           "logic": new(B, O, MS), "X_final": new(B, O, MS), "match_score": new(B, O), "det_score": new(B, O),
+           "n_list": torch.empty(B, device=dev, dtype=torch.int32)}
+    if B * O == 0 or P == 0:
+        for v in out.values():
+            v.zero_()
+        return out
+    if chunks is None:
+        chunks = 1 if os.environ.get("DMM_PIPELINE", "1") == "0" else (4 if B >= 512 else (2 if B >= 128 else 1))
+    chunks = max(1, min(int(chunks), B))
+    chunks = max(chunks, (B + 65534) // 65535)
+    bounds = [(B * i // chunks, B * (i + 1) // chunks) for i in range(chunks)]
+    ws = [torch.empty(max(lib.dmm_mask_iou_workspace_bytes(e - s, P, O, max(HW, 1), 0), 256), device=dev, dtype=torch.uint8)
+          for s, e in bounds]
+    sl = lambda t, s, e: None if t is None else t[s:e]
+
+    def run_chunk(i, k1_after=None):
+        s, e = bounds[i]
+        nb = e - s
+        st = _stream()
+        rc = lib.dmm_cosine_pairwise(_p(tmpl_feat[s:e]), _p(prop_feat[s:e]), nb, T, P, O, D, _p(sl(n_prop, s, e)),
+                                     _p(sl(n_tmpl, s, e)), 1e-8, _p(out["cos"][s:e]), st)
+        _lib.check(rc, "dmm_cosine_pairwise")
+        if k1_after is not None:
+            torch.cuda.current_stream().wait_event(k1_after)        # keep the HBM-bound kernels back to back, not concurrent
+        if k1_events is not None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+        rc = lib.dmm_mask_iou_pairwise(_p(prop_mask[s:e]), P * HW, _p(tmpl_mask[s:e]), O * HW, None, 0, nb, P, O, HW,
+                                       _p(sl(n_prop, s, e)), _p(sl(n_tmpl, s, e)), _p(out["iou"][s:e]), None,
+                                       _p(out["cos"][s:e]), float(1 - w), w, _p(out["sim"][s:e]), None, _p(ws[i]),
+                                       ws[i].numel(), st)
+        _lib.check(rc, "dmm_mask_iou_pairwise")
+        ev = torch.cuda.Event(enable_timing=k1_events is not None)
+        ev.record()
+        if k1_events is not None:
+            k1_events.append((t0, ev))
+        rc = lib.dmm_relax_solve(_p(out["sim"][s:e]), _p(prop_score[s:e]), nb, P, O, _p(sl(n_prop, s, e)),
+                                 _p(sl(n_tmpl, s, e)), int(max_iter), int(proj_iter), float(lr), 1, 1, int(bool(is_test)),
+                                 _p(out["R"][s:e]), _p(out["X_final"][s:e]), _p(out["Bmat"][s:e]), _p(out["logic"][s:e]),
+                                 _p(out["match_score"][s:e]), _p(out["det_score"][s:e]), _p(out["n_list"][s:e]), None, None,
+                                 None, st)
+        _lib.check(rc, "dmm_relax_solve")
+        return ev
+
+    if chunks == 1:
+        run_chunk(0)
+        return out
+    main = torch.cuda.current_stream()
+    start = torch.cuda.Event()
+    start.record(main)
+    side = _side_streams(dev)
+    prev = None
+    for i in range(chunks):
+        st = side[i & 1]
+        if i < 2:
+            st.wait_event(start)
+        with torch.cuda.stream(st):
+            prev = run_chunk(i, prev)
+    for st in side:
+        done = torch.cuda.Event()
+        done.record(st)
+        main.wait_event(done)
+    return out
+
+
 def match_batch(prop_feat: torch.Tensor, prop_mask: torch.Tensor, tmpl_feat: torch.Tensor, tmpl_mask: torch.Tensor,
                 prop_score: torch.Tensor, targets: Optional[torch.Tensor] = None, *, max_iter: int, proj_iter: int,
                 lr: float, score_weight: float, is_test: bool, n_prop=None, n_tmpl=None, row_map=None,
@@ -456,6 +563,16 @@ def match_batch(prop_feat: torch.Tensor, prop_mask: torch.Tensor, tmpl_feat: tor
     H, W = tmpl_mask.shape[-2:]
     dev = tmpl_mask.device
     n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
+    needs_grad = torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad
+                                                 for t in (prop_feat, tmpl_feat, prop_score, prop_mask))
+    if not needs_grad and targets is None and not isinstance(prop_mask, RaggedMasks):
+        out = cost_and_solve(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, max_iter=max_iter, proj_iter=proj_iter,
+                             lr=lr, score_weight=score_weight, is_test=is_test, n_prop=n_prop, n_tmpl=n_tmpl)
+        full = None
+        if apply:
+            full = assign_apply(out["Bmat"], prop_mask, out["logic"], n_prop, n_tmpl, row_map, O_out).view(B, -1, H, W)
+        out.update(full_outmask=full, cost_loss=None)
+        return out
     cos = cosine_pairwise(tmpl_feat, prop_feat, n_prop, n_tmpl)                       # K2
     w = float(score_weight)
     if torch.is_grad_enabled() and cos.requires_grad:

@@ -357,3 +357,24 @@ def test_edge_empty_and_tiny_inputs():
                                    force_len=L)
     for a, b, n in zip(got[:3], want[:3], ("full_outmask", "match_score", "det_score")):
         close(a, b, TOL, n)
+
+
+def test_stream_pipelined_inference_is_bit_identical(monkeypatch):
+    """ops.cost_and_solve cuts large batches into chunks on two staggered side streams; same bits as one stream."""
+    B, P, O, H, W, D = 130, 20, 4, 32, 40, 64
+    pr = make_problems(B, P, O, H, W, D, seed=4242).to(DEV)
+    n_prop = torch.randint(1, P + 1, (B,))
+    n_tmpl = torch.randint(1, O + 1, (B,))
+    kw = dict(max_iter=20, proj_iter=5, lr=0.1, score_weight=0.3, is_test=True, n_prop=n_prop, n_tmpl=n_tmpl)
+    with torch.no_grad():
+        one = ops.cost_and_solve(pr.prop_feat, pr.prop_mask, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score, chunks=1, **kw)
+        for chunks in (2, 3, 4):
+            many = ops.cost_and_solve(pr.prop_feat, pr.prop_mask, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score, chunks=chunks, **kw)
+            torch.cuda.synchronize()
+            for k in one:
+                assert torch.equal(one[k], many[k]), (chunks, k)
+    # and the autograd-capable path (grad enabled, a leaf that requires grad) gives the same numbers
+    ref = ops.match_batch(pr.prop_feat.clone().requires_grad_(True), pr.prop_mask, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score,
+                          max_iter=20, proj_iter=5, lr=0.1, score_weight=0.3, is_test=True, n_prop=n_prop, n_tmpl=n_tmpl)
+    for k in ("sim", "R", "match_score", "det_score"):
+        close(one[k], ref[k], 1e-6, k)
