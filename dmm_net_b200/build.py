@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdmm_b200.so")
-SOURCES = ["abi.cu", "mask_iou.cu", "cosine.cu", "relax_solve.cu", "assign_apply.cu", "roi_mean_pool.cu"]
+SOURCES = ["abi.cu", "mask_iou.cu", "cosine.cu", "relax_solve.cu", "assign_apply.cu", "roi_mean_pool.cu", "host_pack.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-v"]
 
@@ -38,9 +38,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o").replace(".cpp", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src.endswith(".cpp"):   # host-only code (mask packing): host compiler flags, OpenMP
+            cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "-c", os.path.join(CSRC, src), "-o", obj]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, pr in procs:
         out, _ = pr.communicate()
@@ -48,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)

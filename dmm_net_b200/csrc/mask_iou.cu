@@ -594,6 +594,197 @@ extern "C" int dmm_mask_iou_pairwise_ptrs(const float* const* prop_ptrs, int ptr
                       n_prop, n_tmpl, iou, iou2, cos, w_cos, w_iou, sim, counts, workspace, workspace_bytes, stream);
 }
 
+// =========================================================================================================
+// Bit-packed masks.  bit i of word j of a row = (pixel 32*j + i) > 0.5f, zero past the row.
+// The IoU only needs these bits: a producer that packs once (dmm_mask_pack_bits on the device, dmm_host_pack_masks
+// on the host before the PCIe copy) moves 32x fewer bytes through K1.  Same counters, same finalize, same bits out.
+// =========================================================================================================
+namespace dmm {
+namespace {
+
+__global__ void __launch_bounds__(256) mask_pack_bits_kernel(const float* __restrict__ src, long long rows, int HW,
+                                                            uint32_t* __restrict__ dst) {
+  const int words = (HW + 31) / 32;
+  const long long total = rows * words;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long t = warp0; t < total; t += nwarps) {
+    const long long r = t / words;
+    const int j = (int)(t - r * words);
+    const int px = 32 * j + lane;
+    const float v = px < HW ? src[r * HW + px] : 0.f;
+    const uint32_t w = __ballot_sync(0xffffffffu, v > 0.5f);
+    if (lane == 0) dst[t] = w;
+  }
+}
+
+struct PackedParams {
+  const uint32_t* prop; const uint32_t* tmpl; const uint32_t* tmpl2;
+  long long prop_bs, tmpl_bs, tmpl2_bs;   // batch strides in words
+  const int* n_prop; const int* n_tmpl;
+  int P, O, Otot, words;
+  int PT, OT, n_ptiles, n_otiles;
+  int S, chunks_per_slab, n_chunks;       // chunk = 8 words
+  int* ws; int cnt;
+};
+
+template <int TO>
+__global__ void __launch_bounds__(kThreads) mask_iou_partial_packed_kernel(const PackedParams p) {
+  __shared__ const uint32_t* row_ptr[kMaxRows];
+  __shared__ uint32_t bits[2][2][kMaxRows + kTileO][4];
+  __shared__ int red[kTileO * kMaxRows + kMaxRows];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int ptile = blockIdx.z % p.n_ptiles, otile = blockIdx.z / p.n_ptiles;
+  const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
+  const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
+  const int p0 = ptile * p.PT, o0 = otile * p.OT;
+  const int pcnt = min(p.PT, p.P - p0), ocnt = min(p.OT, p.Otot - o0);
+  const int rows = pcnt + ocnt;
+  if (tid < kMaxRows) {
+    const uint32_t* ptr = nullptr;
+    if (tid < pcnt) {
+      if (p0 + tid < np) ptr = p.prop + (long long)b * p.prop_bs + (long long)(p0 + tid) * p.words;
+    } else if (tid < rows) {
+      const int t = o0 + tid - pcnt;
+      if (t < p.O) {
+        if (t < nt) ptr = p.tmpl + (long long)b * p.tmpl_bs + (long long)t * p.words;
+      } else if (t - p.O < nt) {
+        ptr = p.tmpl2 + (long long)b * p.tmpl2_bs + (long long)(t - p.O) * p.words;
+      }
+    }
+    row_ptr[tid] = ptr;   // nullptr: padding row, contributes zero bits
+  }
+  for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kThreads) red[i] = 0;
+  __syncthreads();
+  const int c0 = s * p.chunks_per_slab;
+  const int c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
+  int acc[TO][2];
+#pragma unroll
+  for (int o = 0; o < TO; ++o) acc[o][0] = acc[o][1] = 0;
+  int area0 = 0, area1 = 0;
+  const int grp_b = warp >> 2, word_b = warp & 3;
+  // loader role: threads 0..127 own (row = tid >> 1, group = tid & 1): four words per chunk
+  const int lrow = tid >> 1, lgrp = tid & 1;
+  const uint32_t* lptr = tid < 2 * kMaxRows ? row_ptr[lrow] : nullptr;
+  uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+  auto fetch = [&](int c) {
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (lptr) {
+      const int j = c * 8 + lgrp * 4;
+      if (j + 0 < p.words) w.x = __ldg(lptr + j + 0);
+      if (j + 1 < p.words) w.y = __ldg(lptr + j + 1);
+      if (j + 2 < p.words) w.z = __ldg(lptr + j + 2);
+      if (j + 3 < p.words) w.w = __ldg(lptr + j + 3);
+    }
+    return w;
+  };
+  if (c0 < c1) nxt = fetch(c0);
+  for (int c = c0; c < c1; ++c) {
+    const int buf = (c - c0) & 1;
+    if (tid < 2 * kMaxRows) *reinterpret_cast<uint4*>(&bits[buf][lgrp][lrow][0]) = nxt;
+    if (c + 1 < c1) nxt = fetch(c + 1);
+    __syncthreads();
+    const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
+    area0 += __popc(b0);
+    area1 += __popc(b1);
+#pragma unroll
+    for (int o = 0; o < TO; ++o) {
+      const uint32_t a = bits[buf][grp_b][pcnt + o][word_b];
+      acc[o][0] += __popc(a & b0);
+      acc[o][1] += __popc(a & b1);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < TO; ++o) {
+    if (o < ocnt) {
+      atomicAdd(&red[o * kMaxRows + lane], acc[o][0]);
+      atomicAdd(&red[o * kMaxRows + lane + 32], acc[o][1]);
+    }
+  }
+  atomicAdd(&red[kTileO * kMaxRows + lane], area0);
+  atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
+  __syncthreads();
+  int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
+  for (int i = tid; i < ocnt * pcnt; i += kThreads) {
+    const int o = i / pcnt, q = i - o * pcnt;
+    out[(o0 + o) * p.P + p0 + q] = red[o * kMaxRows + q];
+  }
+  int* area_t = out + p.Otot * p.P;
+  int* area_p = area_t + p.Otot;
+  if (ptile == 0)
+    for (int i = tid; i < ocnt; i += kThreads) area_t[o0 + i] = red[kTileO * kMaxRows + pcnt + i];
+  if (otile == 0)
+    for (int i = tid; i < pcnt; i += kThreads) area_p[p0 + i] = red[kTileO * kMaxRows + i];
+}
+
+}  // namespace
+}  // namespace dmm
+
+extern "C" int dmm_mask_pack_bits(const float* masks, long long rows, int HW, uint32_t* bits, void* stream) {
+  if (rows < 0 || HW < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (rows == 0 || HW == 0) return DMM_OK;
+  if (!masks || !bits) return DMM_ERR_INVALID_ARGUMENT;
+  const long long total = rows * ((HW + 31) / 32);
+  long long blocks = (total + 7) / 8;   // 8 warps per block, one word per warp and trip
+  if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+  mask_pack_bits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(masks, rows, HW, bits);
+  return check_launch();
+}
+
+extern "C" size_t dmm_mask_iou_packed_workspace_bytes(int B, int P, int O, int words, int two_template_sets) {
+  // the packed kernel reuses K1's plan with one "pixel" per bit: chunk = 8 words = 256 bits
+  return dmm_mask_iou_workspace_bytes(B, P, O, words > 0 ? words * 32 : 1, two_template_sets);
+}
+
+extern "C" int dmm_mask_iou_pairwise_packed(const uint32_t* prop_bits, long long prop_bstride_words,
+                                            const uint32_t* tmpl_bits, long long tmpl_bstride_words,
+                                            const uint32_t* tmpl2_bits, long long tmpl2_bstride_words, int B, int P,
+                                            int O, int words, const int* n_prop, const int* n_tmpl, float* iou,
+                                            float* iou2, const float* cos, float w_cos, float w_iou, float* sim,
+                                            int* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || P < 0 || O < 0 || words < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (B == 0 || P == 0 || O == 0) return DMM_OK;
+  if (!workspace || (words > 0 && (!prop_bits || !tmpl_bits))) return DMM_ERR_INVALID_ARGUMENT;
+  if (sim && !cos) return DMM_ERR_INVALID_ARGUMENT;
+  if (iou2 && !tmpl2_bits) return DMM_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
+  const int two = tmpl2_bits != nullptr;
+  const Plan pl = make_plan(B, P, O, words > 0 ? words * 32 : 1, two);
+  if (workspace_bytes < (size_t)B * pl.S * pl.cnt * sizeof(int)) return DMM_ERR_WORKSPACE_TOO_SMALL;
+  if (pl.n_ptiles * pl.n_otiles > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  PackedParams kp;
+  kp.prop = prop_bits; kp.tmpl = tmpl_bits; kp.tmpl2 = tmpl2_bits;
+  kp.prop_bs = prop_bstride_words; kp.tmpl_bs = tmpl_bstride_words; kp.tmpl2_bs = tmpl2_bstride_words;
+  kp.n_prop = n_prop; kp.n_tmpl = n_tmpl; kp.P = P; kp.O = O; kp.Otot = pl.Otot; kp.words = words;
+  kp.PT = pl.PT; kp.OT = pl.OT; kp.n_ptiles = pl.n_ptiles; kp.n_otiles = pl.n_otiles;
+  kp.S = pl.S; kp.chunks_per_slab = pl.chunks_per_slab; kp.n_chunks = pl.n_chunks;
+  kp.ws = (int*)workspace; kp.cnt = pl.cnt;
+  if (words == 0) {
+    DMM_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)B * pl.S * pl.cnt * sizeof(int), st));
+  } else {
+    dim3 grid(pl.S, B, pl.n_ptiles * pl.n_otiles);
+    const int to = pl.OT <= 4 ? 4 : (pl.OT <= 8 ? 8 : (pl.OT <= 12 ? 12 : 16));
+    if (to == 4) mask_iou_partial_packed_kernel<4><<<grid, kThreads, 0, st>>>(kp);
+    else if (to == 8) mask_iou_partial_packed_kernel<8><<<grid, kThreads, 0, st>>>(kp);
+    else if (to == 12) mask_iou_partial_packed_kernel<12><<<grid, kThreads, 0, st>>>(kp);
+    else mask_iou_partial_packed_kernel<16><<<grid, kThreads, 0, st>>>(kp);
+    int rc = check_launch();
+    if (rc) return rc;
+  }
+  FinParams fp;
+  fp.ws = (const int*)workspace; fp.S = pl.S; fp.cnt = pl.cnt; fp.B = B; fp.P = P; fp.O = O; fp.Otot = pl.Otot;
+  fp.n_prop = n_prop; fp.n_tmpl = n_tmpl; fp.iou = iou; fp.iou2 = iou2; fp.cos = cos; fp.w_cos = w_cos;
+  fp.w_iou = w_iou; fp.sim = sim; fp.counts = counts;
+  const long long total = (long long)B * pl.Otot * P;
+  int fblocks = (int)((total + 255) / 256);
+  if (fblocks > 8 * kNumSMs) fblocks = 8 * kNumSMs;
+  mask_iou_finalize_kernel<<<fblocks, 256, 0, st>>>(fp);
+  return check_launch();
+}
+
 extern "C" size_t dmm_mask_iou_rowwise_workspace_bytes(int N, int M) {
   return dmm_mask_iou_workspace_bytes(N, 1, 1, M, 0);
 }

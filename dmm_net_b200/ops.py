@@ -162,6 +162,97 @@ def mask_iou_rowwise(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# bit-packed masks
+# ----------------------------------------------------------------------------------------------------------
+def packed_words(HW: int) -> int:
+    return (int(HW) + 31) // 32
+
+
+def pack_masks_host(masks: torch.Tensor, mask_dims: int = 2, threads: int = 0, out: Optional[torch.Tensor] = None):
+    """HOST fp32 masks [..., H, W] (mask_dims=2) or [..., HW] (mask_dims=1) -> HOST int32 bit planes [..., words]
+    (bit i of word j = pixel 32j+i > 0.5), packed by all host cores (OpenMP + AVX2 inside libdmm_b200).  Pass a pinned
+    ``out`` to make the following H2D copy asynchronous."""
+    lib = _lib.load()
+    assert not masks.is_cuda and masks.dtype == torch.float32
+    masks = masks.contiguous()
+    lead = tuple(masks.shape[:masks.dim() - mask_dims])
+    HW = 1
+    for dsz in masks.shape[masks.dim() - mask_dims:]:
+        HW *= int(dsz)
+    rows = 1
+    for dsz in lead:
+        rows *= int(dsz)
+    words = packed_words(HW)
+    if out is None:
+        out = torch.empty(lead + (words,), dtype=torch.int32)
+    assert out.dtype == torch.int32 and out.is_contiguous() and out.numel() == rows * words
+    rc = lib.dmm_host_pack_masks(_VP(masks.data_ptr()), rows, HW, _VP(out.data_ptr()), int(threads))
+    _lib.check(rc, "dmm_host_pack_masks")
+    return out
+
+
+def pack_masks(masks: torch.Tensor, mask_dims: int = 2) -> torch.Tensor:
+    """DEVICE fp32 masks [..., H, W] -> DEVICE int32 bit planes [..., words]."""
+    lib = _lib.load()
+    masks = _cuda_f32(masks, "masks")
+    lead = tuple(masks.shape[:masks.dim() - mask_dims])
+    HW = 1
+    for dsz in masks.shape[masks.dim() - mask_dims:]:
+        HW *= int(dsz)
+    rows = 1
+    for dsz in lead:
+        rows *= int(dsz)
+    out = torch.empty(lead + (packed_words(HW),), dtype=torch.int32, device=masks.device)
+    if rows * HW > 0:
+        rc = lib.dmm_mask_pack_bits(_p(masks), rows, HW, _p(out), _stream())
+        _lib.check(rc, "dmm_mask_pack_bits")
+    else:
+        out.zero_()
+    return out
+
+
+def mask_iou_pairwise_packed(prop_bits: torch.Tensor, tmpl_bits: torch.Tensor, tmpl2_bits: Optional[torch.Tensor] = None,
+                             n_prop=None, n_tmpl=None, cos: Optional[torch.Tensor] = None, w_cos: float = 0.0,
+                             w_iou: float = 0.0, want_counts: bool = False):
+    """K1 on bit-packed rows: prop_bits [B,P,words], tmpl_bits [B,O,words] (int32, CUDA) -> the dict of mask_iou_pairwise."""
+    lib = _lib.load()
+    for t in (prop_bits, tmpl_bits):
+        assert t.is_cuda and t.dtype == torch.int32 and t.dim() == 3, "packed masks are CUDA int32 [B, rows, words]"
+    prop_bits, tmpl_bits = prop_bits.contiguous(), tmpl_bits.contiguous()
+    B, P, words = prop_bits.shape
+    O = tmpl_bits.shape[1]
+    assert tmpl_bits.shape == (B, O, words)
+    dev = prop_bits.device
+    if tmpl2_bits is not None:
+        tmpl2_bits = tmpl2_bits.contiguous()
+        assert tmpl2_bits.shape == (B, O, words)
+    n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
+    iou = torch.empty(B, O, P, device=dev)
+    iou2 = torch.empty(B, O, P, device=dev) if tmpl2_bits is not None else None
+    sim = None
+    if cos is not None:
+        cos = _cuda_f32(cos, "cos")
+        sim = torch.empty(B, O, P, device=dev)
+    counts = torch.empty(B, O * P + O + P, device=dev, dtype=torch.int32) if want_counts else None
+    out = {"iou": iou, "iou2": iou2, "sim": sim, "counts": counts}
+    if B * P * O == 0:
+        return out
+    step = 65535
+    for s in range(0, B, step):
+        e = min(B, s + step)
+        nb = e - s
+        ws = torch.empty(max(lib.dmm_mask_iou_packed_workspace_bytes(nb, P, O, words, int(tmpl2_bits is not None)), 256),
+                         device=dev, dtype=torch.uint8)
+        sl = lambda t: None if t is None else t[s:e]
+        rc = lib.dmm_mask_iou_pairwise_packed(_p(prop_bits[s:e]), P * words, _p(tmpl_bits[s:e]), O * words, _p(sl(tmpl2_bits)),
+                                              O * words, nb, P, O, words, _p(sl(n_prop)), _p(sl(n_tmpl)), _p(iou[s:e]),
+                                              _p(sl(iou2)), _p(sl(cos)), float(w_cos), float(w_iou), _p(sl(sim)),
+                                              _p(sl(counts)), _p(ws), ws.numel(), _stream())
+        _lib.check(rc, "dmm_mask_iou_pairwise_packed")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 # K2  cosine
 # ----------------------------------------------------------------------------------------------------------
 class _CosineFn(torch.autograd.Function):
@@ -451,7 +542,8 @@ def cost_and_solve(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, ma
     back to back while the latency-bound cosine of the next chunk and the solver of the previous chunk run underneath
     them (the TMA K1 kernel leaves registers and shared memory for one solver CTA per SM).  Every output is allocated
     on the caller's stream, which waits for both side streams before returning, so results and memory lifetimes are
-    exactly those of the single-stream order; ``DMM_PIPELINE=0`` or ``chunks=1`` disables the overlap.
+    exactly those of the single-stream order.  Off by default (it measured slower, see below); ``chunks=N`` or
+    ``DMM_PIPELINE=1`` enables it.
     ``k1_events``: optional list that receives one (start, end) CUDA-event pair per K1 launch, recorded on the stream
     the kernel runs on (bench.py's roofline timing).
     Returns dict(sim, cos, iou, R, Bmat, logic, X_final, match_score, det_score, n_list)."""
@@ -481,7 +573,10 @@ def cost_and_solve(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, ma
             v.zero_()
         return out
     if chunks is None:
-        chunks = 1 if os.environ.get("DMM_PIPELINE", "1") == "0" else (4 if B >= 512 else (2 if B >= 128 else 1))
+        # measured on B200 (profiles/README.md): 4 staggered chunks of 256 problems run 4.34 ms vs 4.14 ms for one launch
+        # of 1024 -- smaller K1 launches pay more tail, and the co-running solver slows K1 more than it hides.  So the
+        # overlap is opt-in (DMM_PIPELINE=1); the default is one chunk per 65535 problems.
+        chunks = (4 if B >= 512 else (2 if B >= 128 else 1)) if os.environ.get("DMM_PIPELINE", "0") == "1" else 1
     chunks = max(1, min(int(chunks), B))
     chunks = max(chunks, (B + 65534) // 65535)
     bounds = [(B * i // chunks, B * (i + 1) // chunks) for i in range(chunks)]

@@ -71,6 +71,24 @@ int dmm_mask_iou_pairwise_ptrs(const float* const* prop_ptrs, int ptrs_aligned16
                                float w_cos, float w_iou, float* sim, int* counts, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* ---- bit-packed masks ----------------------------------------------------------------
+ * bit i of word j of a row = (pixel 32*j + i) > 0.5f, zero past the row end; a row is dmm_packed_words(HW) uint32.
+ * The IoU needs only these bits, so a producer that packs once moves 32x fewer bytes through K1:
+ *   dmm_mask_pack_bits      device fp32 [rows][HW] -> device bits [rows][words]
+ *   dmm_host_pack_masks     HOST fp32 -> HOST bits, multi-threaded (threads <= 0: all cores), so that masks held in
+ *                           host memory cross PCIe as 0.86 MB instead of 27.5 MB per match
+ *   dmm_mask_iou_pairwise_packed   K1 on packed rows: same outputs, bit-identical to dmm_mask_iou_pairwise. */
+long long dmm_packed_words(long long HW);
+int dmm_host_pack_masks(const float* src_host, long long rows, long long HW, uint32_t* dst_host, int threads);
+int dmm_mask_pack_bits(const float* masks, long long rows, int HW, uint32_t* bits, void* stream);
+size_t dmm_mask_iou_packed_workspace_bytes(int B, int P, int O, int words, int two_template_sets);
+int dmm_mask_iou_pairwise_packed(const uint32_t* prop_bits, long long prop_bstride_words, const uint32_t* tmpl_bits,
+                                 long long tmpl_bstride_words, const uint32_t* tmpl2_bits,
+                                 long long tmpl2_bstride_words, int B, int P, int O, int words, const int* n_prop,
+                                 const int* n_tmpl, float* iou, float* iou2, const float* cos, float w_cos,
+                                 float w_iou, float* sim, int* counts, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* Row-paired IoU: a[N][M] vs b[N][M] -> iou[N]  (compute_iou_binary_mask_2D itself; callers trainer.py:190,298). */
 size_t dmm_mask_iou_rowwise_workspace_bytes(int N, int M);
 int dmm_mask_iou_rowwise(const float* a, const float* b, int N, int M, float* iou, void* workspace,

@@ -23,7 +23,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert os.path.exists(path)
     lib = ctypes.CDLL(path)
     names = header_functions()
-    assert len(names) >= 22
+    assert len(names) >= 27
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dmm_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)

@@ -378,3 +378,23 @@ def test_stream_pipelined_inference_is_bit_identical(monkeypatch):
                           max_iter=20, proj_iter=5, lr=0.1, score_weight=0.3, is_test=True, n_prop=n_prop, n_tmpl=n_tmpl)
     for k in ("sim", "R", "match_score", "det_score"):
         close(one[k], ref[k], 1e-6, k)
+
+
+@pytest.mark.parametrize("P,O,H,W", [(50, 10, 64, 112), (9, 3, 7, 9), (70, 12, 10, 33), (5, 2, 1, 31)])
+def test_bit_packed_masks_same_iou(P, O, H, W):
+    """K1 on bit-packed rows (device packer or host packer) gives the bits of the fp32 path."""
+    pr = make_problems(2, P, O, H, W, 8, seed=11 * P + O, with_targets=True)
+    d = pr.to(DEV)
+    n_prop = torch.tensor([P, max(1, P - 3)])
+    want = ops.mask_iou_pairwise(d.prop_mask, d.tmpl_mask, d.targets, n_prop=n_prop, want_counts=True)
+    pb, tb, gb = ops.pack_masks(d.prop_mask), ops.pack_masks(d.tmpl_mask), ops.pack_masks(d.targets)
+    assert pb.shape == (2, P, ops.packed_words(H * W)) and pb.dtype == torch.int32
+    hb = ops.pack_masks_host(pr.prop_mask)                       # host packer == device packer
+    assert torch.equal(hb, pb.cpu())
+    got = ops.mask_iou_pairwise_packed(pb, tb, gb, n_prop=n_prop, want_counts=True)
+    for k in ("iou", "iou2"):
+        assert torch.equal(want[k], got[k]), k
+    for b in range(2):
+        wb = orc.pairwise_binary_iou(pr.prop_mask[b, :int(n_prop[b])].reshape(int(n_prop[b]), -1),
+                                     pr.tmpl_mask[b].reshape(O, -1), expand=False)
+        np.testing.assert_array_equal(got["iou"][b, :, :int(n_prop[b])].cpu().numpy(), wb.numpy())
