@@ -98,6 +98,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def tune_cpu_threads(one):
+    """Give the CPU baseline the thread count it runs fastest with: boxes of this pool expose 128 logical CPUs under a
+    16-CPU cgroup quota, where torch with 128 threads is several times SLOWER than with 16-32."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        one()
+        t0 = time.perf_counter()
+        one()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_rate(seconds_budget: float, threads: int):
     """The reference's CPU path (oracle port: same torch-CPU op sequence incl. the [O*P,HW] expansions) on this
     host's cores: cost-build + solve of the headline problem, timed one problem at a time."""
@@ -112,7 +130,7 @@ def cpu_reference_rate(seconds_budget: float, threads: int):
             _, _, X_list, _ = orc.relax_solve(-sim, MAX_ITER, PROJ_ITER, LR)
             return sum(X_list) / len(X_list)
 
-    one()                                                            # warm-up
+    threads = tune_cpu_threads(one)                                   # also warms up
     n, t0 = 0, time.perf_counter()
     while True:
         one()
@@ -120,7 +138,7 @@ def cpu_reference_rate(seconds_budget: float, threads: int):
         el = time.perf_counter() - t0
         if el >= seconds_budget or n >= 200:
             break
-    return n / el, n, el
+    return n / el, n, el, threads
 
 
 def run_reference(args, rank, world):
@@ -140,7 +158,7 @@ def run_reference(args, rank, world):
             sim, _ = orc.cost_matrix(pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, SCORE_W, None, expand=True)
             orc.relax_solve(-sim, MAX_ITER, PROJ_ITER, LR)
 
-    one()
+    threads = tune_cpu_threads(one)
     t0 = time.perf_counter(); one(); t_one = time.perf_counter() - t0
     per_step = max(1, int(per_step_budget / max(t_one, 1e-3)))
     for _ in range(args.warmup):
@@ -171,7 +189,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="independent problems per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (rank 0, N=1)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -237,17 +255,20 @@ def main():
     from dmm_net_b200.modules.match_model import MatchModel
     from dmm_net_b200.synth import default_cfg
     layer = MatchModel(default_cfg(MAX_ITER, PROJ_ITER, LR, SCORE_W), is_test=1)
-    Be = min(B, 32)
+    Be = min(B, 64)
     host = {k: getattr(pr, k)[:Be].cpu().pin_memory() for k in ("prop_feat", "prop_mask", "tmpl_feat", "tmpl_mask", "prop_score")}
-    h2d = sum(v.numel() * 4 for v in host.values())
     res_host = torch.empty(Be, O, max(P, O + 1), pin_memory=True)
     res_ms = torch.empty(Be, O, pin_memory=True)
+    e2e_info = {}
 
     def e2e_step():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        out = layer.forward_many(d["prop_feat"], d["prop_mask"], d["tmpl_feat"], d["tmpl_mask"], d["prop_score"])
+        # the reference-facing call with HOST buffers: host cores bit-pack the masks, bits+features cross PCIe,
+        # K2 -> K1(packed) -> K3 on the device, the assignment and scores come back to pinned host memory
+        out = layer.forward_many_host(host["prop_feat"], host["prop_mask"], host["tmpl_feat"], host["tmpl_mask"],
+                                      host["prop_score"], device=dev)
         res_host.copy_(out["R"], non_blocking=True)
         res_ms.copy_(out["match_score"], non_blocking=True)
+        e2e_info.update(h2d=out["h2d_bytes"], packed=out["host_packed_bytes"], threads=out["host_threads"])
 
     with torch.no_grad():
         e2e_step()
@@ -255,18 +276,23 @@ def main():
         if world > 1:
             dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_step()                                                    # second warm-up: pinned staging buffers exist now
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter()
         a.record()
         for _ in range(args.e2e_steps):
             e2e_step()
         b.record()
         torch.cuda.synchronize()
-        e2e_ms = a.elapsed_time(b)
+        # host work (mask packing) sits inside the region: take the larger of the device-event span and the wall clock
+        e2e_ms = max(a.elapsed_time(b), (time.perf_counter() - t_wall) * 1e3)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item()
     e2e_val = world * Be * args.e2e_steps / (e2e_ms * 1e-3)
     d2h = (res_host.numel() + res_ms.numel()) * 4
+    h2d = e2e_info.get("h2d", 0)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -280,7 +306,10 @@ def main():
                        "full_step_gbs_per_gpu": ALGO_BYTES_PER_MATCH * B / (ms_total / args.steps * 1e-3) / 1e9},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "matches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "problems_per_step": Be, "api": "MatchModel.forward_many on pinned host tensors (+assignment-apply)"},
+                    "problems_per_step": Be, "host_bytes_packed_per_step": e2e_info.get("packed"),
+                    "host_threads": e2e_info.get("threads"),
+                    "api": "MatchModel.forward_many_host: pinned host fp32 inputs, masks bit-packed by the host cores, "
+                           "bits+features+scores H2D, R and match_score D2H"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "mask_iou_partial_kernel(+finalize)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -288,7 +317,7 @@ def main():
         }
         if world == 1 and args.cpu_seconds > 0:
             threads = os.cpu_count() or 1
-            rate, n, el = cpu_reference_rate(args.cpu_seconds, threads)
+            rate, n, el, threads = cpu_reference_rate(args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "matches/s", "cores": threads, "kind": "port",
                                     "sample": f"{n} problems of the headline shape in {el:.1f} s, oracle/match_oracle.py "
                                               f"(torch-CPU port of the reference op sequence incl. [O*P,HW] expansion)"}

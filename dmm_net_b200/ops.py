@@ -697,3 +697,73 @@ def match_batch(prop_feat: torch.Tensor, prop_mask: torch.Tensor, tmpl_feat: tor
         full = assign_apply(Bm, prop_mask, logic, n_prop, n_tmpl, row_map, O_out).view(B, -1, H, W)   # K4
     return {"full_outmask": full, "match_score": ms, "det_score": ds, "sim": sim, "R": R, "Bmat": Bm, "logic": logic,
             "n_list": n_list, "cost_loss": cost_loss, "cos": cos, "iou": r["iou"], "X_final": Xf}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# host-buffer entry: masks held in HOST memory cross PCIe as bits
+# ----------------------------------------------------------------------------------------------------------
+_PINNED = {}
+
+
+def host_threads() -> int:
+    """Threads for host-side packing: the cgroup CPU quota when there is one (x2, packing is memory-bound), else all cores.
+    (On the round-1 GPU box: 128 logical CPUs but cpu.max = 16 CPUs; 32-64 threads pack at 200-340 GB/s, 128 collapse.)"""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(4, 2 * int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def _pinned(key, shape, dtype):
+    t = _PINNED.get(key)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        t = torch.empty(shape, dtype=dtype).pin_memory()
+        _PINNED[key] = t
+    return t
+
+
+def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, max_iter: int, proj_iter: int, lr: float,
+                     score_weight: float, is_test: bool, device="cuda", threads: Optional[int] = None, n_prop=None,
+                     n_tmpl=None):
+    """cost-build + solve for a batch whose inputs live in HOST memory (CPU fp32 tensors, pinned or not).
+
+    The IoU needs only the thresholded bits, so the host cores pack the masks (OpenMP + AVX2, memory speed) and only
+    bits + features + scores cross PCIe: 0.98 MB instead of 27.65 MB per match at the headline size.  Device side:
+    K2 cosine -> K1 on packed rows (+finalize/mix) -> K3 solver+head.  Returns the dict of ``cost_and_solve`` (device
+    tensors; ``iou``/``sim`` are bit-identical to the fp32-mask path).  The soft masks stay on the host: the
+    assignment-apply (which needs <= O selected rows per problem) is left to the caller / ``match_batch``."""
+    lib = _lib.load()
+    for t in (prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score):
+        assert not t.is_cuda and t.dtype == torch.float32, "match_batch_host takes CPU fp32 tensors"
+    if tmpl_feat.dim() == 3:
+        tmpl_feat = tmpl_feat.unsqueeze(1)
+    dev = torch.device(device)
+    B, P = prop_mask.shape[:2]
+    O = tmpl_mask.shape[1]
+    HW = 1
+    for dsz in prop_mask.shape[2:]:
+        HW *= int(dsz)
+    words = packed_words(HW)
+    th = host_threads() if threads is None else int(threads)
+    pb = pack_masks_host(prop_mask.reshape(B, P, HW), mask_dims=1, threads=th, out=_pinned("pb", (B, P, words), torch.int32))
+    tb = pack_masks_host(tmpl_mask.reshape(B, O, HW), mask_dims=1, threads=th, out=_pinned("tb", (B, O, words), torch.int32))
+    to_dev = lambda t: t.to(dev, non_blocking=True)
+    pbd, tbd = to_dev(pb), to_dev(tb)
+    pf, tf, sc = to_dev(prop_feat.contiguous()), to_dev(tmpl_feat.contiguous()), to_dev(prop_score.contiguous())
+    n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
+    with torch.no_grad():
+        cos = cosine_pairwise(tf, pf, n_prop, n_tmpl)
+        w = float(score_weight)
+        r = mask_iou_pairwise_packed(pbd, tbd, None, n_prop, n_tmpl, cos=cos, w_cos=1 - w, w_iou=w)
+        R, Bm, ms, ds, Xf, logic, n_list = relax_solve(r["sim"], sc, n_prop, n_tmpl, max_iter, proj_iter, lr, True, True,
+                                                       bool(is_test))
+    return {"cos": cos, "iou": r["iou"], "sim": r["sim"], "R": R, "Bmat": Bm, "logic": logic, "X_final": Xf,
+            "match_score": ms, "det_score": ds, "n_list": n_list,
+            "h2d_bytes": 4 * (pb.numel() + tb.numel() + prop_feat.numel() + tmpl_feat.numel() + prop_score.numel()),
+            "host_packed_bytes": 4 * (prop_mask.numel() + tmpl_mask.numel()), "host_threads": th}
+

@@ -398,3 +398,18 @@ def test_bit_packed_masks_same_iou(P, O, H, W):
         wb = orc.pairwise_binary_iou(pr.prop_mask[b, :int(n_prop[b])].reshape(int(n_prop[b]), -1),
                                      pr.tmpl_mask[b].reshape(O, -1), expand=False)
         np.testing.assert_array_equal(got["iou"][b, :, :int(n_prop[b])].cpu().numpy(), wb.numpy())
+
+
+def test_host_buffer_entry_matches_device_path():
+    """MatchModel.forward_many_host (masks bit-packed by the host cores before PCIe) == forward_many on device tensors."""
+    B, P, O, H, W, D = 5, 50, 10, 64, 112, 64
+    pr = make_problems(B, P, O, H, W, D, seed=808)
+    layer = MatchModel(default_cfg(20, 5), is_test=1)
+    d = pr.to(DEV)
+    with torch.no_grad():
+        want = layer.forward_many(d.prop_feat, d.prop_mask, d.tmpl_feat, d.tmpl_mask, d.prop_score)
+    got = layer.forward_many_host(pr.prop_feat, pr.prop_mask, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score, threads=4)
+    torch.cuda.synchronize()
+    for k in ("iou", "sim", "R", "Bmat", "match_score", "det_score", "n_list"):
+        assert torch.equal(want[k], got[k]), k
+    assert got["h2d_bytes"] < 0.1 * got["host_packed_bytes"]
