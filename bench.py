@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads for mask packing (0: cgroup-aware default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -265,7 +266,7 @@ def main():
         # the reference-facing call with HOST buffers: host cores bit-pack the masks, bits+features cross PCIe,
         # K2 -> K1(packed) -> K3 on the device, the assignment and scores come back to pinned host memory
         out = layer.forward_many_host(host["prop_feat"], host["prop_mask"], host["tmpl_feat"], host["tmpl_mask"],
-                                      host["prop_score"], device=dev)
+                                      host["prop_score"], device=dev, threads=args.e2e_threads or None)
         res_host.copy_(out["R"], non_blocking=True)
         res_ms.copy_(out["match_score"], non_blocking=True)
         e2e_info.update(h2d=out["h2d_bytes"], packed=out["host_packed_bytes"], threads=out["host_threads"])
