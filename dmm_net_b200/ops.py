@@ -706,14 +706,15 @@ _PINNED = {}
 
 
 def host_threads() -> int:
-    """Threads for host-side packing: the cgroup CPU quota when there is one (x2, packing is memory-bound), else all cores.
-    (On the round-1 GPU box: 128 logical CPUs but cpu.max = 16 CPUs; 32-64 threads pack at 200-340 GB/s, 128 collapse.)"""
+    """Threads for host-side packing: the cgroup CPU quota when there is one, else all cores.
+    (Round-1 GPU box: 128 logical CPUs under cpu.max = 16 CPUs.  Short bursts pack at 340 GB/s with 64 threads, but
+    sustained the quota throttles: e2e 3.8k matches/s with 16 threads, 3.0k with 32, 1.5k with 64, 0.8k with 96.)"""
     import os
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
         if quota != "max":
-            n = min(n, max(4, 2 * int(int(quota) / int(period))))
+            n = min(n, max(2, int(int(quota) / int(period))))
     except Exception:
         pass
     return max(1, n)
