@@ -31,6 +31,11 @@ with torch.no_grad():
 full_bytes = B * ((P + O) * H * W * 4 + 2 * O * H * W * 4)
 print(f"full layer (eval 20x5, +apply) B={B}: {ms:.3f} ms -> {B / ms * 1e3:.0f} matches/s, {full_bytes / ms / 1e6:.0f} GB/s (masks once + apply rows)")
 
+one = pr.squeeze0()
+with torch.no_grad():
+    ms = timeit(lambda: layer_t(one.prop_feat, one.prop_mask, [one.tmpl_feat], one.tmpl_mask, one.prop_score), reps=20)
+print(f"single-problem MatchModel.forward (the reference's per-video call, eval 20x5, incl. python + 5 launches): {ms * 1e3:.0f} us")
+
 layer_tr = MatchModel(default_cfg(10, 5), is_test=0)
 pf = pr.prop_feat.clone().requires_grad_(True)
 tf = pr.tmpl_feat.clone().requires_grad_(True)
