@@ -38,6 +38,7 @@ struct IouParams {
   int P, O, Otot, HW;
   int PT, OT, n_ptiles, n_otiles;  // tile sizes / counts
   int S, chunks_per_slab, n_chunks;
+  int B_items;                     // problems in this launch (the persistent TMA kernel walks S * B_items items)
   int* ws;                         // [B][S][cnt]
   int cnt;                         // Otot*P + Otot + P
 };
@@ -251,6 +252,10 @@ template <int TO>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorMap tm_prop,
                             const __grid_constant__ CUtensorMap tm_tmpl, const __grid_constant__ CUtensorMap tm_tmpl2) {
+  // PERSISTENT: one CTA per SM walks work items (problem b, pixel slab s) = blockIdx.x, +gridDim.x, ...  The stage ring
+  // and its mbarrier phases run on across items, so the producer is already filling the next item's stages while the
+  // consumers reduce and write the previous item's counters: no pipeline fill/drain per slab (with one CTA per SM
+  // there is no second CTA to hide it), and the static striding balances the SMs to within one small item.
   constexpr int TH = TO / 2;                                      // template counters per warp half
   extern __shared__ unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -260,9 +265,9 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
   __shared__ __align__(8) unsigned long long empty_bar[kStages];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = blockIdx.x, b = blockIdx.y;
   const int pcnt = p.P, ocnt = p.Otot;                            // single tile (checked on the host)
   const bool two = p.tmpl2 != nullptr;
+  const int n_items = p.S * p.B_items;
 
   for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kTmaThreads) red[i] = 0;
   if (tid == 0) {
@@ -275,98 +280,109 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
   }
   __syncthreads();   // the only CTA-wide barrier: the producer warp never joins another one
 
-  const int c0 = s * p.chunks_per_slab;
-  const int c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
-  const int nchunks = max(c1 - c0, 0);
-
   if (warp == kTmaConsWarps) {
-    // ---- producer: one elected lane keeps the ring full --------------------------------------------------
+    // ---- producer: one elected lane keeps the ring full, across items ------------------------------------
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(pcnt + ocnt) * kChunkPx * 4u;   // full boxes: OOB pixels are zero-filled
-      for (int i = 0; i < nchunks; ++i) {
-        const int st = i % kStages;
-        if (i >= kStages) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((i / kStages) - 1) & 1));
-        const uint32_t bar = smem_u32(&full_bar[st]);
-        const uint32_t dst = smem_u32(stage + (size_t)st * kStageFloats);
-        const int px0 = (c0 + i) * kChunkPx;
-        mbar_expect_tx(bar, bytes);
-        tma_load_3d(dst, &tm_prop, px0, 0, b, bar);
-        tma_load_3d(dst + (uint32_t)pcnt * kChunkPx * 4u, &tm_tmpl, px0, 0, b, bar);
-        if (two) tma_load_3d(dst + (uint32_t)(pcnt + p.O) * kChunkPx * 4u, &tm_tmpl2, px0, 0, b, bar);
+      unsigned g = 0;                                                   // chunks issued by this CTA so far
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / p.S, s = item - b * p.S;
+        const int c0 = s * p.chunks_per_slab, c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
+        for (int c = c0; c < c1; ++c, ++g) {
+          const unsigned st = g % kStages;
+          if (g >= kStages) mbar_wait(smem_u32(&empty_bar[st]), ((g / kStages) - 1u) & 1u);
+          const uint32_t bar = smem_u32(&full_bar[st]);
+          const uint32_t dst = smem_u32(stage + (size_t)st * kStageFloats);
+          const int px0 = c * kChunkPx;
+          mbar_expect_tx(bar, bytes);
+          tma_load_3d(dst, &tm_prop, px0, 0, b, bar);
+          tma_load_3d(dst + (uint32_t)pcnt * kChunkPx * 4u, &tm_tmpl, px0, 0, b, bar);
+          if (two) tma_load_3d(dst + (uint32_t)(pcnt + p.O) * kChunkPx * 4u, &tm_tmpl2, px0, 0, b, bar);
+        }
       }
     }
     return;
   }
 
   // ---- consumers ---------------------------------------------------------------------------------------------
-  int acc[TH][2];
-#pragma unroll
-  for (int o = 0; o < TH; ++o) acc[o][0] = acc[o][1] = 0;
-  int area0 = 0, area1 = 0;
   const int word = warp & 7, half = warp >> 3;
   const int grp_b = word >> 2, word_b = word & 3;
   const int lane_px = lane * 4;
-
-  for (int i = 0; i < nchunks; ++i) {
-    const int st = i % kStages, buf = i & 1;
-    mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((i / kStages) & 1));
-    const float* sbase = stage + (size_t)st * kStageFloats;
-    // ---- phase A: landed stage -> bit planes (8 row pieces per warp) --------------------------------------
-    // rows >= pcnt+ocnt of the stage are never written by the TMA: stale bits, counted into counters nobody reads
+  unsigned g = 0;                                                 // chunks consumed by this CTA so far
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / p.S, s = item - b * p.S;
+    const int c0 = s * p.chunks_per_slab, c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
+    int acc[TH][2];
 #pragma unroll
-    for (int k = 0; k < kTmaUnits; ++k) {
-      const int u = warp + kTmaConsWarps * k;
-      const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
-      uint4 w;
-      w.x = __ballot_sync(0xffffffffu, v.x > 0.5f);
-      w.y = __ballot_sync(0xffffffffu, v.y > 0.5f);
-      w.z = __ballot_sync(0xffffffffu, v.z > 0.5f);
-      w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
-      *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
+    for (int o = 0; o < TH; ++o) acc[o][0] = acc[o][1] = 0;
+    int area0 = 0, area1 = 0;
+
+    for (int c = c0; c < c1; ++c, ++g) {
+      const unsigned st = g % kStages, buf = g & 1u;
+      mbar_wait(smem_u32(&full_bar[st]), (g / kStages) & 1u);
+      const float* sbase = stage + (size_t)st * kStageFloats;
+      // ---- phase A: landed stage -> bit planes (8 row pieces per warp) ------------------------------------
+      // rows >= pcnt+ocnt of the stage are never written by the TMA: stale bits, counted into counters nobody reads
+#pragma unroll
+      for (int k = 0; k < kTmaUnits; ++k) {
+        const int u = warp + kTmaConsWarps * k;
+        const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
+        uint4 w;
+        w.x = __ballot_sync(0xffffffffu, v.x > 0.5f);
+        w.y = __ballot_sync(0xffffffffu, v.y > 0.5f);
+        w.z = __ballot_sync(0xffffffffu, v.z > 0.5f);
+        w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
+        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
+      }
+      // this warp is done with the stage (its loads fed the ballots above): hand it back to the producer
+      if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
+      consumer_barrier();
+      // ---- phase B: 16 warps = 8 words x 2 halves of the template rows -------------------------------------
+      {
+        const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
+        if (half == 0) {
+          area0 += __popc(b0);
+          area1 += __popc(b1);
+        }
+#pragma unroll
+        for (int o = 0; o < TH; ++o) {
+          const uint32_t a = bits[buf][grp_b][pcnt + half * TH + o][word_b];
+          acc[o][0] += __popc(a & b0);
+          acc[o][1] += __popc(a & b1);
+        }
+      }
+      // double-buffered bit planes: buffer `buf` is rewritten two chunks later, after the next chunk's barrier
     }
-    // this warp is done with the stage (its loads fed the ballots above): hand it back to the producer
-    if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
+
+    // ---- item epilogue (the producer keeps loading the next item meanwhile) ----------------------------------
+#pragma unroll
+    for (int o = 0; o < TH; ++o) {
+      const int oo = half * TH + o;
+      if (oo < ocnt) {
+        atomicAdd(&red[oo * kMaxRows + lane], acc[o][0]);
+        atomicAdd(&red[oo * kMaxRows + lane + 32], acc[o][1]);
+      }
+    }
+    if (half == 0) {
+      atomicAdd(&red[kTileO * kMaxRows + lane], area0);
+      atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
+    }
     consumer_barrier();
-    // ---- phase B: 16 warps = 8 words x 2 halves of the template rows ---------------------------------------
-    {
-      const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
-      if (half == 0) {
-        area0 += __popc(b0);
-        area1 += __popc(b1);
-      }
-#pragma unroll
-      for (int o = 0; o < TH; ++o) {
-        const uint32_t a = bits[buf][grp_b][pcnt + half * TH + o][word_b];
-        acc[o][0] += __popc(a & b0);
-        acc[o][1] += __popc(a & b1);
-      }
+    int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
+    for (int i = tid; i < ocnt * pcnt; i += kTmaConsThreads) {
+      const int o = i / pcnt, q = i - o * pcnt;
+      out[o * p.P + q] = red[o * kMaxRows + q];
     }
-    // double-buffered bit planes: buffer `buf` is rewritten in iteration i+2, after the barrier of iteration i+1
+    int* area_t = out + p.Otot * p.P;
+    int* area_p = area_t + p.Otot;
+    for (int i = tid; i < ocnt; i += kTmaConsThreads) area_t[i] = red[kTileO * kMaxRows + pcnt + i];
+    for (int i = tid; i < pcnt; i += kTmaConsThreads) area_p[i] = red[kTileO * kMaxRows + i];
+    consumer_barrier();
+    for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kTmaConsThreads) red[i] = 0;
+    // the next item's first atomics come after at least one chunk barrier (every item has >= 1 chunk); an item
+    // without chunks would race here, so guard it:
+    if (c1 <= c0) consumer_barrier();
   }
-
-#pragma unroll
-  for (int o = 0; o < TH; ++o) {
-    const int oo = half * TH + o;
-    if (oo < ocnt) {
-      atomicAdd(&red[oo * kMaxRows + lane], acc[o][0]);
-      atomicAdd(&red[oo * kMaxRows + lane + 32], acc[o][1]);
-    }
-  }
-  if (half == 0) {
-    atomicAdd(&red[kTileO * kMaxRows + lane], area0);
-    atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
-  }
-  consumer_barrier();
-
-  int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
-  for (int i = tid; i < ocnt * pcnt; i += kTmaConsThreads) {
-    const int o = i / pcnt, q = i - o * pcnt;
-    out[o * p.P + q] = red[o * kMaxRows + q];
-  }
-  int* area_t = out + p.Otot * p.P;
-  int* area_p = area_t + p.Otot;
-  for (int i = tid; i < ocnt; i += kTmaConsThreads) area_t[i] = red[kTileO * kMaxRows + pcnt + i];
-  for (int i = tid; i < pcnt; i += kTmaConsThreads) area_p[i] = red[kTileO * kMaxRows + i];
 }
 
 // ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) -------------------
@@ -407,7 +423,9 @@ int launch_tma(const IouParams& kp, const CUtensorMap& mp, const CUtensorMap& mt
   cudaError_t e = cudaFuncSetAttribute(mask_iou_partial_tma_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kTmaDynSmem);
   if (e != cudaSuccess) { set_last_cuda_error((int)e); return DMM_ERR_CUDA; }
-  mask_iou_partial_tma_kernel<TO><<<grid, kTmaThreads, kTmaDynSmem, st>>>(kp, mp, mt, mt2);
+  const long long items = (long long)grid.x * grid.y;   // S * B work items, one persistent CTA per SM walks them
+  const int nctas = (int)(items < kNumSMs ? items : kNumSMs);
+  mask_iou_partial_tma_kernel<TO><<<nctas, kTmaThreads, kTmaDynSmem, st>>>(kp, mp, mt, mt2);
   return check_launch();
 }
 
@@ -477,9 +495,10 @@ Plan make_plan(int B, int P, int O, int HW, int two) {
   pl.n_otiles = (pl.Otot + pl.OT - 1) / pl.OT;
   pl.n_chunks = (HW + kChunkPx - 1) / kChunkPx;
   if (pl.n_chunks < 1) pl.n_chunks = 1;
-  // enough CTAs for ~4 waves at 2 CTAs/SM, but never slabs shorter than 4 chunks
+  // ~24 work items per SM (the persistent TMA kernel strides over them: imbalance <= one small item; the LDG
+  // kernel gets 12 waves of 2 CTAs/SM), but never slabs shorter than 4 chunks
   const long long tiles = (long long)B * pl.n_ptiles * pl.n_otiles;
-  long long want = (4LL * 2 * kNumSMs + tiles - 1) / tiles;
+  long long want = (24LL * kNumSMs + tiles - 1) / tiles;
   long long max_s = pl.n_chunks / 4 > 0 ? pl.n_chunks / 4 : 1;
   long long S = want < 1 ? 1 : (want > max_s ? max_s : want);
   if (S > 65535) S = 65535;
@@ -524,6 +543,7 @@ static int run_pairwise(const float* prop, const float* const* prop_ptrs, int pt
   kp.P = P; kp.O = O; kp.Otot = pl.Otot; kp.HW = HW;
   kp.PT = pl.PT; kp.OT = pl.OT; kp.n_ptiles = pl.n_ptiles; kp.n_otiles = pl.n_otiles;
   kp.S = pl.S; kp.chunks_per_slab = pl.chunks_per_slab; kp.n_chunks = pl.n_chunks;
+  kp.B_items = B;
   kp.ws = (int*)workspace; kp.cnt = pl.cnt;
 
   if (HW == 0) {  // empty masks: every count is 0 -> IoU 0/(0+1e-6) = 0; skip the streaming kernel
