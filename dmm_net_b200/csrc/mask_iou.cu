@@ -39,6 +39,7 @@ struct IouParams {
   int PT, OT, n_ptiles, n_otiles;  // tile sizes / counts
   int S, chunks_per_slab, n_chunks;
   int B_items;                     // problems in this launch (the persistent TMA kernel walks S * B_items items)
+  int* item_counter;               // zeroed per launch: dynamic work distribution of the persistent TMA kernel
   int* ws;                         // [B][S][cnt]
   int cnt;                         // Otot*P + Otot + P
 };
@@ -252,10 +253,10 @@ template <int TO>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorMap tm_prop,
                             const __grid_constant__ CUtensorMap tm_tmpl, const __grid_constant__ CUtensorMap tm_tmpl2) {
-  // PERSISTENT: one CTA per SM walks work items (problem b, pixel slab s) = blockIdx.x, +gridDim.x, ...  The stage ring
+  // PERSISTENT: one CTA per SM claims work items (problem b, pixel slab s) from an atomic counter.  The stage ring
   // and its mbarrier phases run on across items, so the producer is already filling the next item's stages while the
   // consumers reduce and write the previous item's counters: no pipeline fill/drain per slab (with one CTA per SM
-  // there is no second CTA to hide it), and the static striding balances the SMs to within one small item.
+  // there is no second CTA to hide it).
   constexpr int TH = TO / 2;                                      // template counters per warp half
   extern __shared__ unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -263,6 +264,8 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
   __shared__ int red[kTileO * kMaxRows + kMaxRows];
   __shared__ __align__(8) unsigned long long full_bar[kStages];
   __shared__ __align__(8) unsigned long long empty_bar[kStages];
+  __shared__ int stage_item[kStages];   // work item of the chunk in each stage (-1: stop), written by the producer
+  __shared__ int stage_last[kStages];   // 1 when that chunk is the last of its item
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pcnt = p.P, ocnt = p.Otot;                            // single tile (checked on the host)
@@ -282,10 +285,20 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
 
   if (warp == kTmaConsWarps) {
     // ---- producer: one elected lane keeps the ring full, across items ------------------------------------
+    // Items are claimed dynamically (atomic counter): SMs on the far die stream ~10 % slower, a static split would
+    // run at the pace of the slowest SM (measured: 6.9 TB/s static vs 7.2 TB/s with the hardware CTA scheduler).
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(pcnt + ocnt) * kChunkPx * 4u;   // full boxes: OOB pixels are zero-filled
       unsigned g = 0;                                                   // chunks issued by this CTA so far
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      while (true) {
+        const int item = atomicAdd(p.item_counter, 1);
+        if (item >= n_items) {                                          // sentinel stage: tells the consumers to stop
+          const unsigned st = g % kStages;
+          if (g >= kStages) mbar_wait(smem_u32(&empty_bar[st]), ((g / kStages) - 1u) & 1u);
+          stage_item[st] = -1;
+          mbar_arrive(smem_u32(&full_bar[st]));
+          break;
+        }
         const int b = item / p.S, s = item - b * p.S;
         const int c0 = s * p.chunks_per_slab, c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
         for (int c = c0; c < c1; ++c, ++g) {
@@ -294,6 +307,8 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
           const uint32_t bar = smem_u32(&full_bar[st]);
           const uint32_t dst = smem_u32(stage + (size_t)st * kStageFloats);
           const int px0 = c * kChunkPx;
+          stage_item[st] = item;                                        // published by the arrive below (release)
+          stage_last[st] = (c == c1 - 1);
           mbar_expect_tx(bar, bytes);
           tma_load_3d(dst, &tm_prop, px0, 0, b, bar);
           tma_load_3d(dst + (uint32_t)pcnt * kChunkPx * 4u, &tm_tmpl, px0, 0, b, bar);
@@ -309,50 +324,50 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
   const int grp_b = word >> 2, word_b = word & 3;
   const int lane_px = lane * 4;
   unsigned g = 0;                                                 // chunks consumed by this CTA so far
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int b = item / p.S, s = item - b * p.S;
-    const int c0 = s * p.chunks_per_slab, c1 = min(c0 + p.chunks_per_slab, p.n_chunks);
-    int acc[TH][2];
+  int acc[TH][2];
 #pragma unroll
-    for (int o = 0; o < TH; ++o) acc[o][0] = acc[o][1] = 0;
-    int area0 = 0, area1 = 0;
-
-    for (int c = c0; c < c1; ++c, ++g) {
-      const unsigned st = g % kStages, buf = g & 1u;
-      mbar_wait(smem_u32(&full_bar[st]), (g / kStages) & 1u);
-      const float* sbase = stage + (size_t)st * kStageFloats;
-      // ---- phase A: landed stage -> bit planes (8 row pieces per warp) ------------------------------------
-      // rows >= pcnt+ocnt of the stage are never written by the TMA: stale bits, counted into counters nobody reads
+  for (int o = 0; o < TH; ++o) acc[o][0] = acc[o][1] = 0;
+  int area0 = 0, area1 = 0;
+  while (true) {
+    const unsigned st = g % kStages, buf = g & 1u;
+    mbar_wait(smem_u32(&full_bar[st]), (g / kStages) & 1u);
+    const int item = stage_item[st];
+    if (item < 0) break;                                          // sentinel: no more work
+    const bool last = stage_last[st] != 0;
+    const float* sbase = stage + (size_t)st * kStageFloats;
+    // ---- phase A: landed stage -> bit planes (8 row pieces per warp) --------------------------------------
+    // rows >= pcnt+ocnt of the stage are never written by the TMA: stale bits, counted into counters nobody reads
 #pragma unroll
-      for (int k = 0; k < kTmaUnits; ++k) {
-        const int u = warp + kTmaConsWarps * k;
-        const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
-        uint4 w;
-        w.x = __ballot_sync(0xffffffffu, v.x > 0.5f);
-        w.y = __ballot_sync(0xffffffffu, v.y > 0.5f);
-        w.z = __ballot_sync(0xffffffffu, v.z > 0.5f);
-        w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
-        *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
-      }
-      // this warp is done with the stage (its loads fed the ballots above): hand it back to the producer
-      if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
-      consumer_barrier();
-      // ---- phase B: 16 warps = 8 words x 2 halves of the template rows -------------------------------------
-      {
-        const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
-        if (half == 0) {
-          area0 += __popc(b0);
-          area1 += __popc(b1);
-        }
-#pragma unroll
-        for (int o = 0; o < TH; ++o) {
-          const uint32_t a = bits[buf][grp_b][pcnt + half * TH + o][word_b];
-          acc[o][0] += __popc(a & b0);
-          acc[o][1] += __popc(a & b1);
-        }
-      }
-      // double-buffered bit planes: buffer `buf` is rewritten two chunks later, after the next chunk's barrier
+    for (int k = 0; k < kTmaUnits; ++k) {
+      const int u = warp + kTmaConsWarps * k;
+      const float4 v = *reinterpret_cast<const float4*>(sbase + (u >> 1) * kChunkPx + (u & 1) * 128 + lane_px);
+      uint4 w;
+      w.x = __ballot_sync(0xffffffffu, v.x > 0.5f);
+      w.y = __ballot_sync(0xffffffffu, v.y > 0.5f);
+      w.z = __ballot_sync(0xffffffffu, v.z > 0.5f);
+      w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
+      *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
     }
+    // this warp is done with the stage (its loads fed the ballots above): hand it back to the producer
+    if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
+    consumer_barrier();
+    // ---- phase B: 16 warps = 8 words x 2 halves of the template rows ---------------------------------------
+    {
+      const uint32_t b0 = bits[buf][grp_b][lane][word_b], b1 = bits[buf][grp_b][lane + 32][word_b];
+      if (half == 0) {
+        area0 += __popc(b0);
+        area1 += __popc(b1);
+      }
+#pragma unroll
+      for (int o = 0; o < TH; ++o) {
+        const uint32_t a = bits[buf][grp_b][pcnt + half * TH + o][word_b];
+        acc[o][0] += __popc(a & b0);
+        acc[o][1] += __popc(a & b1);
+      }
+    }
+    ++g;
+    // double-buffered bit planes: buffer `buf` is rewritten two chunks later, after the next chunk's barrier
+    if (!last) continue;
 
     // ---- item epilogue (the producer keeps loading the next item meanwhile) ----------------------------------
 #pragma unroll
@@ -362,12 +377,15 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
         atomicAdd(&red[oo * kMaxRows + lane], acc[o][0]);
         atomicAdd(&red[oo * kMaxRows + lane + 32], acc[o][1]);
       }
+      acc[o][0] = acc[o][1] = 0;
     }
     if (half == 0) {
       atomicAdd(&red[kTileO * kMaxRows + lane], area0);
       atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
     }
+    area0 = area1 = 0;
     consumer_barrier();
+    const int b = item / p.S, s = item - b * p.S;
     int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
     for (int i = tid; i < ocnt * pcnt; i += kTmaConsThreads) {
       const int o = i / pcnt, q = i - o * pcnt;
@@ -379,9 +397,7 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
     for (int i = tid; i < pcnt; i += kTmaConsThreads) area_p[i] = red[kTileO * kMaxRows + i];
     consumer_barrier();
     for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kTmaConsThreads) red[i] = 0;
-    // the next item's first atomics come after at least one chunk barrier (every item has >= 1 chunk); an item
-    // without chunks would race here, so guard it:
-    if (c1 <= c0) consumer_barrier();
+    // the next epilogue's atomics come after at least one more chunk barrier: the zeroing above is ordered before them
   }
 }
 
@@ -516,7 +532,7 @@ using namespace dmm;
 extern "C" size_t dmm_mask_iou_workspace_bytes(int B, int P, int O, int HW, int two_template_sets) {
   if (B <= 0 || P <= 0 || O <= 0 || HW <= 0) return 0;
   const Plan pl = make_plan(B, P, O, HW, two_template_sets);
-  return align_up((size_t)B * pl.S * pl.cnt * sizeof(int), 256);
+  return align_up((size_t)B * pl.S * pl.cnt * sizeof(int), 256) + 256;   // + the persistent kernel's work counter
 }
 
 static int run_pairwise(const float* prop, const float* const* prop_ptrs, int ptrs_aligned16, long long prop_bstride,
@@ -532,11 +548,13 @@ static int run_pairwise(const float* prop, const float* const* prop_ptrs, int pt
   if (B > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
   const int two = tmpl2 != nullptr;
   const Plan pl = make_plan(B, P, O, HW > 0 ? HW : 1, two);
-  if (workspace_bytes < (size_t)B * pl.S * pl.cnt * sizeof(int)) return DMM_ERR_WORKSPACE_TOO_SMALL;
+  const size_t counts_bytes = align_up((size_t)B * pl.S * pl.cnt * sizeof(int), 256);
+  if (workspace_bytes < counts_bytes + 256) return DMM_ERR_WORKSPACE_TOO_SMALL;
   if (pl.n_ptiles * pl.n_otiles > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
 
   IouParams kp;
+  kp.item_counter = (int*)((char*)workspace + counts_bytes);
   kp.prop = prop; kp.prop_ptrs = prop_ptrs; kp.tmpl = tmpl; kp.tmpl2 = tmpl2;
   kp.prop_bs = prop_bstride; kp.tmpl_bs = tmpl_bstride; kp.tmpl2_bs = tmpl2_bstride;
   kp.n_prop = n_prop; kp.n_tmpl = n_tmpl;
@@ -568,6 +586,7 @@ static int run_pairwise(const float* prop, const float* const* prop_ptrs, int pt
   int rc = DMM_OK;
   if (HW == 0) {
   } else if (use_tma) {
+    DMM_CUDA_TRY(cudaMemsetAsync(kp.item_counter, 0, sizeof(int), st));
     rc = to == 4 ? launch_tma<4>(kp, mp, mt, mt2, grid, st) : to == 8 ? launch_tma<8>(kp, mp, mt, mt2, grid, st)
        : to == 12 ? launch_tma<12>(kp, mp, mt, mt2, grid, st) : launch_tma<16>(kp, mp, mt, mt2, grid, st);
   } else {
