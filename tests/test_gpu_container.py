@@ -137,3 +137,16 @@ def test_ragged_pointer_table_equals_stacked_batch():
     (ops.assign_apply(Bm, pr.prop_mask, ref["logic"], n_prop=n_prop) * w).sum().backward()
     (ops.assign_apply(Bm2, plist, ref["logic"]) * w).sum().backward()
     assert torch.allclose(Bm.grad, Bm2.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_synthetic_clip_loop_runs_sequential_frames():
+    """examples/synthetic_clip_eval.py: the eval-shaped loop (templates of frame t+1 = matched masks of frame t)."""
+    import argparse
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "synthetic_clip_eval.py")
+    spec = importlib.util.spec_from_file_location("synthetic_clip_eval", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rate = mod.run(argparse.Namespace(clips=3, frames=4, proposals=9, objects=3, size=[64, 96]))
+    assert rate > 0
