@@ -453,3 +453,34 @@ def test_randomized_shapes_against_oracle():
             close(out["det_score"][b, :o], ds, TOL, tag + " det_score")
             if tg is not None:
                 close(out["cost_loss"][b], loss["cost_loss"], 1e-5, tag + " cost_loss")
+
+
+def test_inference_path_is_cuda_graph_capturable():
+    """No host sync, no allocation outside torch's pool, no illegal call inside the ABI: the whole cost-build + solve +
+    apply chain can be captured once and replayed on new data written into the same buffers."""
+    B, P, O, H, W, D = 6, 50, 10, 64, 112, 64
+    a = make_problems(B, P, O, H, W, D, seed=1).to(DEV)
+    b = make_problems(B, P, O, H, W, D, seed=2).to(DEV)
+    kw = dict(max_iter=20, proj_iter=5, lr=0.1, score_weight=0.3, is_test=True)
+    static = [t.clone() for t in (a.prop_feat, a.prop_mask, a.tmpl_feat, a.tmpl_mask, a.prop_score)]
+    with torch.no_grad():
+        want_a = ops.match_batch(a.prop_feat, a.prop_mask, a.tmpl_feat, a.tmpl_mask, a.prop_score, **kw)
+        want_b = ops.match_batch(b.prop_feat, b.prop_mask, b.tmpl_feat, b.tmpl_mask, b.prop_score, **kw)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                              # warm-up on a side stream, as torch requires
+            ops.match_batch(*static, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = ops.match_batch(*static, **kw)
+        graph.replay()
+        torch.cuda.synchronize()
+        for k in ("sim", "R", "full_outmask", "match_score", "det_score"):
+            assert torch.equal(out[k], want_a[k]), k
+        for dst, src in zip(static, (b.prop_feat, b.prop_mask, b.tmpl_feat, b.tmpl_mask, b.prop_score)):
+            dst.copy_(src)
+        graph.replay()
+        torch.cuda.synchronize()
+        for k in ("sim", "R", "full_outmask", "match_score", "det_score"):
+            assert torch.equal(out[k], want_b[k]), k
