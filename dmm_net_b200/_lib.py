@@ -49,6 +49,10 @@ SIGNATURES = {
                                   _vp]),
     "dmm_roi_mean_pool": (_i, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, _vp, _vp]),
     "dmm_roi_mean_pool_bwd": (_i, [_vp, POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, POINTER(c_void_p), _vp]),
+    "dmm_mask_pyramid_level_size": (_i, [_i, _i, _i, POINTER(c_int), POINTER(c_int)]),
+    "dmm_mask_pyramid": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, POINTER(c_void_p), _vp]),
+    "dmm_mask_pyramid_bwd": (_i, [POINTER(c_void_p), _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dmm_merge_labels": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -521,6 +521,97 @@ def roi_mean_pool(features: Sequence[torch.Tensor], rois: torch.Tensor) -> torch
 
 
 # ----------------------------------------------------------------------------------------------------------
+# K6 / K7  rows after the layer: decoder mask-input pyramid, merged label map, hard-IoU metric
+# ----------------------------------------------------------------------------------------------------------
+def _bohw(t: torch.Tensor, name: str, B: int, O: int, H: int, W: int) -> torch.Tensor:
+    """[B,O,H,W] or [B,O,HW] fp32 CUDA whose (O,H,W) block is dense; the batch stride may be larger (a view)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"dmm_net_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)")
+    assert t.shape[0] == B and t.shape[1] == O and t.numel() == B * O * H * W, (name, tuple(t.shape), (B, O, H, W))
+    t = t.float().reshape(B, O, H * W)
+    if t.stride(2) != 1 or t.stride(1) != H * W:
+        t = t.contiguous()
+    return t
+
+
+class _PyramidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prev, ref, init, H, W, L):
+        lib = _lib.load()
+        B, O = init.shape[:2]
+        sizes = []
+        for k in range(L):
+            hk, wk = ctypes.c_int(), ctypes.c_int()
+            _lib.check(lib.dmm_mask_pyramid_level_size(H, W, k, ctypes.byref(hk), ctypes.byref(wk)), "dmm_mask_pyramid_level_size")
+            sizes.append((hk.value, wk.value))
+        outs = [torch.empty(O, B, 3, hk, wk, device=init.device) for hk, wk in sizes]
+        if B * O * H * W > 0 and L > 0:
+            ptrs = (ctypes.c_void_p * L)(*[o.data_ptr() for o in outs])
+            rc = lib.dmm_mask_pyramid(_p(prev), prev.stride(0), _p(ref), ref.stride(0), _p(init), init.stride(0), B, O, H, W,
+                                      L, ptrs, _stream())
+            _lib.check(rc, "dmm_mask_pyramid")
+        ctx.save_for_backward(prev, ref, init)
+        ctx.dims = (H, W, L)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        lib = _lib.load()
+        prev, ref, init = ctx.saved_tensors
+        H, W, L = ctx.dims
+        B, O = init.shape[:2]
+        gs = [None if g is None else g.contiguous().float() for g in g_outs]
+        grads = [torch.empty(B, O, H * W, device=init.device) if ctx.needs_input_grad[i] else None for i in range(3)]
+        if B * O * H * W > 0 and any(g is not None for g in grads):
+            ptrs = (ctypes.c_void_p * max(L, 1))(*[None if g is None else g.data_ptr() for g in gs])
+            rc = lib.dmm_mask_pyramid_bwd(ptrs, _p(prev), prev.stride(0), _p(ref), ref.stride(0), _p(init), init.stride(0),
+                                          B, O, H, W, L, _p(grads[0]), _p(grads[1]), _p(grads[2]), _stream())
+            _lib.check(rc, "dmm_mask_pyramid_bwd")
+        return grads[0], grads[1], grads[2], None, None, None
+
+
+def mask_pyramid(prev_mask: torch.Tensor, ref_mask: torch.Tensor, init_pred: torch.Tensor, n_levels: int = 4):
+    """The decoder's mask inputs for EVERY object in one pass (trainer.py:256-263, evaluator.py:187-194).
+
+    prev_mask / ref_mask / init_pred: [B,O,H,W] (or [B,O,HW] for the first two, as the reference holds them).
+    Returns ``n_levels`` tensors [O,B,3,hk,wk], finest first (window 4, 8, ...): ``levels[k][t]`` is what the reference
+    calls ``mask_lstm`` (before its ``reversed``) entry k of object t.  Differentiable w.r.t. all three inputs."""
+    assert init_pred.dim() == 4, "init_pred_inst is [B,O,H,W]"
+    B, O, H, W = init_pred.shape
+    init = _bohw(init_pred, "init_pred_inst", B, O, H, W)
+    prev = _bohw(prev_mask, "prev_mask", B, O, H, W)
+    ref = _bohw(ref_mask, "ref_mask", B, O, H, W)
+    return list(_PyramidFn.apply(prev, ref, init, int(H), int(W), int(n_levels)))
+
+
+def merge_labels(outs: torch.Tensor, n_valid=None) -> torch.Tensor:
+    """outs [B,O,HW] (or [B,O,H,W]) sigmoid masks -> uint8 label map [B,HW]: 0 = background, t+1 = object t
+    (evaluator.py:139-145, for all videos of the batch at once; ``n_valid[b]`` = tplt_valid_batch[b].sum())."""
+    lib = _lib.load()
+    if not outs.is_cuda:
+        raise RuntimeError("dmm_net_b200: `outs` must be a CUDA tensor (there is no CPU fallback)")
+    B, O = outs.shape[:2]
+    o3 = outs.float().reshape(B, O, -1)
+    if o3.stride(2) != 1 or (O > 1 and o3.stride(1) != o3.shape[2]):
+        o3 = o3.contiguous()
+    HW = o3.shape[2]
+    label = torch.empty(B, HW, dtype=torch.uint8, device=outs.device)
+    if B * HW > 0:
+        rc = lib.dmm_merge_labels(_p(o3), o3.stride(0), B, O, HW, _p(_counts(n_valid, B, outs.device)), _p(label), _stream())
+        _lib.check(rc, "dmm_merge_labels")
+    return label
+
+
+def hard_iou_mean(y_mask: torch.Tensor, pred: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
+    """trainer.py:189-196 / :296-300: mean hard IoU over the valid templates.  The [B*O] row-paired IoU is K1's row-wise
+    entry; the [B,O] masking and the scalar mean are left to torch (50 numbers)."""
+    B, O = valid.shape
+    iou = mask_iou_rowwise(y_mask.reshape(B * O, -1), pred.reshape(B * O, -1)).view(B, O) * valid.float()
+    n = valid.sum()
+    return torch.where(n > 0, iou.sum() / (n + 1e-6), iou.sum() * 0)
+
+
+# ----------------------------------------------------------------------------------------------------------
 # the fused layer over a batch of problems
 # ----------------------------------------------------------------------------------------------------------
 _SIDE_STREAMS = {}

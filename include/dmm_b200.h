@@ -175,6 +175,33 @@ int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], const int Wl[
 int dmm_roi_mean_pool_bwd(const float* g_out, const int Hl[4], const int Wl[4], int N, int C, const float* rois,
                           int R, float* const g_feat[4], void* stream);
 
+/* ---- K6: decoder mask-input pyramid -------------------------------------------------
+ * Replaces, for every object at once, trainer.py:256-263 / evaluator.py:187-194:
+ *   prev_m_inst = cat(prev_mask[:,t], ref_mask[:,t], init_pred_inst[:,t]) -> [B,3,H,W];
+ *   nn.MaxPool2d((2,2), ceil_mode=True) applied 1+L times, the last L results kept.
+ * prev / ref / init: [B][O][H][W] (batch strides in elements, object stride H*W).
+ * out_levels: HOST array of L device pointers; level k (window 4<<k) is [O][B][3][hk][wk] with
+ * hk = ceil(H / (4<<k)), wk = ceil(W / (4<<k)) (dmm_mask_pyramid_level_size), so out_levels[k] + t*B*3*hk*wk is the
+ * reference's mask_lstm entry of object t (the reference list is reversed: coarsest first).  L <= 5.  Bit-exact.
+ */
+int dmm_mask_pyramid_level_size(int H, int W, int level, int* h_out, int* w_out);
+int dmm_mask_pyramid(const float* prev, long long prev_bstride, const float* ref, long long ref_bstride,
+                     const float* init, long long init_bstride, int B, int O, int H, int W, int L,
+                     float* const* out_levels, void* stream);
+/* Backward: g_out_levels[k] (may be NULL = zero cotangent) in the layout of out_levels; g_prev / g_ref / g_init
+ * dense [B][O][H][W], overwritten, each may be NULL.  Gradients go to the first maximum of every 2x2 stage in
+ * row-major order (max_pool2d_with_indices); deterministic, bit-equal to autograd through the chained pools. */
+int dmm_mask_pyramid_bwd(const float* const* g_out_levels, const float* prev, long long prev_bstride, const float* ref,
+                         long long ref_bstride, const float* init, long long init_bstride, int B, int O, int H, int W,
+                         int L, float* g_prev, float* g_ref, float* g_init, void* stream);
+
+/* ---- K7: merged label map ------------------------------------------------------------------------------------
+ * Replaces evaluator.py:139-145: label[b,px] = argmax([1 - max_o m[b,o,px], m[b,0,px], ..., m[b,n-1,px]]) with
+ * n = n_valid[b] (NULL: O) valid objects; first maximum wins; n == 0 gives 0.  masks [B][O][HW] -> label uint8 [B][HW].
+ */
+int dmm_merge_labels(const float* masks, long long bstride, int B, int O, int HW, const int* n_valid,
+                     unsigned char* label, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
