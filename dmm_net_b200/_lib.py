@@ -53,6 +53,9 @@ SIGNATURES = {
     "dmm_mask_pyramid": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, POINTER(c_void_p), _vp]),
     "dmm_mask_pyramid_bwd": (_i, [POINTER(c_void_p), _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dmm_merge_labels": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
+    "dmm_paste_masks_workspace_bytes": (_sz, [_i]),
+    "dmm_paste_masks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dmm_box_nms": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

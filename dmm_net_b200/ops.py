@@ -612,6 +612,53 @@ def hard_iou_mean(y_mask: torch.Tensor, pred: torch.Tensor, valid: torch.Tensor)
 
 
 # ----------------------------------------------------------------------------------------------------------
+# K8 / K9  rows before the layer: proposal paste (+ bit rows + tight boxes), box NMS
+# ----------------------------------------------------------------------------------------------------------
+def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, im_h: int, im_w: int, thresh: float = 0.5, padding: int = 1,
+                want_pasted: bool = True, want_bits: bool = False, want_tight: bool = True):
+    """masks [N,1,M,M] or [N,M,M] soft, boxes [N,4] xyxy -> dict(pasted [N,im_h,im_w], bits [N,words] int32, tight [N,4]
+    int64), every proposal of a batch of frames in one launch (masker.py:91-206).  ``pasted`` rows are what K1 / K4 read;
+    ``bits`` rows are the packed-K1 format."""
+    lib = _lib.load()
+    masks, boxes = _cuda_f32(masks, "masks"), _cuda_f32(boxes, "boxes")
+    N, M = masks.shape[0], masks.shape[-1]
+    assert masks.numel() == N * M * M and boxes.shape == (N, 4), (tuple(masks.shape), tuple(boxes.shape))
+    dev = masks.device
+    pasted = torch.empty(N, im_h, im_w, device=dev) if want_pasted else None
+    bits = torch.empty(N, packed_words(im_h * im_w), dtype=torch.int32, device=dev) if want_bits else None
+    tight = torch.empty(N, 4, dtype=torch.int64, device=dev) if want_tight else None
+    out = {"pasted": pasted, "bits": bits, "tight": tight}
+    for s in range(0, N, 65535):
+        e = min(N, s + 65535)
+        ws = torch.empty(max(lib.dmm_paste_masks_workspace_bytes(e - s), 256), device=dev, dtype=torch.uint8)
+        sl = lambda t: None if t is None else t[s:e]
+        rc = lib.dmm_paste_masks(_p(masks[s:e]), _p(boxes[s:e]), e - s, M, int(padding), int(im_h), int(im_w), float(thresh),
+                                 _p(sl(pasted)), _p(sl(bits)), _p(sl(tight)), _p(ws), ws.numel(), _stream())
+        _lib.check(rc, "dmm_paste_masks")
+    return out
+
+
+def box_nms(boxes: torch.Tensor, scores: torch.Tensor, thresh: float, max_keep: int = 0, n_boxes=None):
+    """boxes [F,n,4] (or [n,4]), scores [F,n] (or [n]) -> (keep [F,n] int64 kept indices in score order, -1 padded; n_keep
+    [F] int32).  Greedy NMS with the legacy +1 widths, one CTA per frame (boxlist_ops.py:15-29)."""
+    lib = _lib.load()
+    single = boxes.dim() == 2
+    boxes = _cuda_f32(boxes, "boxes")
+    scores = _cuda_f32(scores, "scores")
+    if single:
+        boxes, scores = boxes[None], scores[None]
+    F_, n = scores.shape
+    assert boxes.shape == (F_, n, 4), (tuple(boxes.shape), tuple(scores.shape))
+    keep = torch.empty(F_, n, dtype=torch.int64, device=boxes.device)
+    n_keep = torch.zeros(F_, dtype=torch.int32, device=boxes.device)
+    if F_ > 0:
+        rc = lib.dmm_box_nms(_p(boxes), _p(scores), _p(_counts(n_boxes, F_, boxes.device)), F_, n, float(thresh),
+                             int(max_keep), _p(keep), _p(n_keep), _stream())
+        _lib.check(rc, "dmm_box_nms")
+    return keep, n_keep
+
+
+# ----------------------------------------------------------------------------------------------------------
 # the fused layer over a batch of problems
 # ----------------------------------------------------------------------------------------------------------
 _SIDE_STREAMS = {}

@@ -1,6 +1,7 @@
 """Minimal stand-in for maskrcnn_benchmark.structures.bounding_box.BoxList (un-vendored dependency of the
 reference): just what the matching path touches -- ``bbox`` [n,4] xyxy, ``get_field/add_field/fields`` and ``len``
-(dmm/modules/dmm_model.py:59-71,106-123; dmm/modules/feature_extractor.py:32-37)."""
+(dmm/modules/dmm_model.py:59-71,106-123; dmm/modules/feature_extractor.py:32-37) plus ``boxlist[keep]`` for
+``filter_results`` (dmm/utils/boxlist_ops.py:28)."""
 import torch
 
 
@@ -28,6 +29,12 @@ class BoxList(object):
         out = BoxList(self.bbox.to(device), self.size, self.mode)
         for k, v in self.extra_fields.items():
             out.add_field(k, v.to(device) if hasattr(v, "to") else v)
+        return out
+
+    def __getitem__(self, item):
+        out = BoxList(self.bbox[item], self.size, self.mode)
+        for k, v in self.extra_fields.items():
+            out.add_field(k, v[item])
         return out
 
     def __len__(self):

@@ -202,6 +202,32 @@ int dmm_mask_pyramid_bwd(const float* const* g_out_levels, const float* prev, lo
 int dmm_merge_labels(const float* masks, long long bstride, int B, int O, int HW, const int* n_valid,
                      unsigned char* label, void* stream);
 
+/* ---- K8: proposal mask paste ----------------------------------------------------------
+ * Replaces Masker.forward_single_image / paste_mask_in_image / binmask_to_box (dmm/utils/masker.py:91-206) for all N
+ * proposals of a batch of frames in one launch.  masks [N][M][M] soft, boxes [N][4] xyxy (image pixels), padding >= 1.
+ * Outputs (each may be NULL):
+ *   pasted [N][im_h][im_w] fp32 -- the zero-padded mask bilinearly resized (align_corners=False) to the expanded int
+ *          box and pasted into a zero image; these are the dense proposal rows K1 / K4 read;
+ *   bits   [N][dmm_packed_words(im_h*im_w)] -- (pasted > 0.5f) in the packed-row format of dmm_mask_iou_pairwise_packed;
+ *   tight  [N][4] int64 -- binmask_to_box(pasted > thresh): xmin, ymin, xmax, ymax, or 0, 0, im_h, im_w when empty.
+ * workspace: dmm_paste_masks_workspace_bytes(N) bytes, needed when tight != NULL.  M + 2*padding <= 64.
+ * A box entirely outside the image pastes nothing (the reference raises there).
+ */
+size_t dmm_paste_masks_workspace_bytes(int N);
+int dmm_paste_masks(const float* masks, const float* boxes, int N, int M, int padding, int im_h, int im_w, float thresh,
+                    float* pasted, uint32_t* bits, long long* tight, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- K9: box NMS ---------------------------------------------------------------------------------------------
+ * Replaces filter_results (dmm/utils/boxlist_ops.py:15-29) -> maskrcnn_benchmark.layers.nms (un-vendored): greedy,
+ * score-descending (ties: lower index first), IoU with the legacy +1 pixel widths, suppress when IoU > thresh, then
+ * keep at most max_keep (<= 0: all).  One CTA per frame.
+ * boxes [F][n_max][4], scores [F][n_max], n_boxes [F] (NULL: n_max) -> keep [F][n_max] int64 (kept indices in score
+ * order, -1 padded), n_keep [F].  n_max <= 1024.
+ */
+int dmm_box_nms(const float* boxes, const float* scores, const int* n_boxes, int F, int n_max, float thresh,
+                int max_keep, long long* keep, int* n_keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
