@@ -35,6 +35,7 @@ SIGNATURES = {
     "dmm_mask_iou_rowwise_workspace_bytes": (_sz, [_i, _i]),
     "dmm_mask_iou_rowwise": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dmm_cosine_pairwise": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp]),
+    "dmm_cosine_pairwise_impl": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp]),
     "dmm_cosine_pairwise_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "dmm_relax_saved_bytes": (_sz, [_i, _i, _i]),
     "dmm_relax_solve": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -4,9 +4,12 @@
 // averaged over the template-feature sets (dmm/modules/match_model.py:72-76; one set in practice,
 // dmm/modules/dmm_model.py:44).  ATen normalises each vector by max(||v||, eps) first, multiplies, then sums.
 //
-// 0.5 MFLOP and 123 KB per match next to 27.5 MB of masks: this kernel is deliberately plain fp32 FFMA
-// (a TF32 tensor-core contraction would break the 1e-4 parity bar for nothing).  One CTA per problem; the
-// normalised template rows of a tile sit in shared memory, each warp owns proposals.
+// This file holds the plain fp32 FFMA forward (general shapes, several template sets, ~3e-7 of fp64) and the backward;
+// the default forward for the shapes the layer runs is the tcgen05 3xTF32 kernel in cosine_tc.cu (~3e-6 of fp64).
+// One CTA per problem; the feature tiles sit in shared memory, lanes are proposals.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace dmm {
@@ -304,6 +307,24 @@ __global__ void __launch_bounds__(kThreads) cosine_bwd_kernel(const CosParams p)
 
 using namespace dmm;
 
+namespace dmm {
+int cosine_tc_try_launch(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
+                         const int* n_prop, const int* n_tmpl, float eps, float* cos, cudaStream_t st);   // cosine_tc.cu
+}
+
+// Default implementation of the forward: the tcgen05 kernel wherever its envelope allows (T == 1, P <= 64, O <= 16,
+// D >= 32 and a multiple of 4, 16-byte aligned features), else the fp32 FFMA kernel.  DMM_K2_IMPL=simt|tc overrides the
+// default for dmm_cosine_pairwise (read once); dmm_cosine_pairwise_impl selects per call.
+static int k2_default_impl() {
+  static const int impl = [] {
+    const char* e = getenv("DMM_K2_IMPL");
+    if (e && !strcmp(e, "simt")) return DMM_COSINE_SIMT;
+    if (e && !strcmp(e, "tc")) return DMM_COSINE_TC;
+    return DMM_COSINE_AUTO;
+  }();
+  return impl;
+}
+
 static int fill_params(CosParams& kp, const float* q, const float* k, int B, int T, int P, int O, int D,
                        const int* n_prop, const int* n_tmpl, float eps) {
   if (B < 0 || T < 1 || P < 0 || O < 0 || D < 0) return DMM_ERR_INVALID_ARGUMENT;
@@ -314,18 +335,32 @@ static int fill_params(CosParams& kp, const float* q, const float* k, int B, int
   return DMM_OK;
 }
 
-extern "C" int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
-                                   const int* n_prop, const int* n_tmpl, float eps, float* cos, void* stream) {
+extern "C" int dmm_cosine_pairwise_impl(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
+                                        const int* n_prop, const int* n_tmpl, float eps, float* cos, int impl,
+                                        void* stream) {
   CosParams kp;
   int rc = fill_params(kp, tmpl_feat, prop_feat, B, T, P, O, D, n_prop, n_tmpl, eps);
   if (rc) return rc;
+  if (impl != DMM_COSINE_AUTO && impl != DMM_COSINE_SIMT && impl != DMM_COSINE_TC) return DMM_ERR_INVALID_ARGUMENT;
   if (B == 0 || P == 0 || O == 0) return DMM_OK;
   if (!tmpl_feat || !prop_feat || !cos) return DMM_ERR_INVALID_ARGUMENT;
   kp.cos = cos;
   if (P > kMaxP) return DMM_ERR_UNSUPPORTED_SHAPE;
+  if (impl != DMM_COSINE_SIMT) {
+    rc = D >= 32 ? cosine_tc_try_launch(tmpl_feat, prop_feat, B, T, P, O, D, n_prop, n_tmpl, eps, cos, (cudaStream_t)stream) : -1;
+    if (rc >= 0) return rc;            // launched (or a CUDA error); -1: outside the tensor-core kernel's envelope
+    if (impl == DMM_COSINE_TC) return DMM_ERR_UNSUPPORTED_SHAPE;
+  }
   DMM_CUDA_TRY(cudaFuncSetAttribute(cosine_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCosSmem));
   cosine_fwd_kernel<<<B, kThreads, kCosSmem, (cudaStream_t)stream>>>(kp);
   return check_launch();
+}
+
+extern "C" int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
+                                   const int* n_prop, const int* n_tmpl, float eps, float* cos, void* stream) {
+  int impl = k2_default_impl();
+  if (impl == DMM_COSINE_TC) impl = DMM_COSINE_AUTO;   // the env override never turns an unsupported shape into an error
+  return dmm_cosine_pairwise_impl(tmpl_feat, prop_feat, B, T, P, O, D, n_prop, n_tmpl, eps, cos, impl, stream);
 }
 
 extern "C" int dmm_cosine_pairwise_bwd(const float* g_cos, const float* cos_fwd, const float* tmpl_feat,

@@ -257,14 +257,18 @@ def mask_iou_pairwise_packed(prop_bits: torch.Tensor, tmpl_bits: torch.Tensor, t
 # ----------------------------------------------------------------------------------------------------------
 class _CosineFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tmpl_feat, prop_feat, n_prop, n_tmpl, eps):
+    def forward(ctx, tmpl_feat, prop_feat, n_prop, n_tmpl, eps, impl):
         lib = _lib.load()
         B, T, O, D = tmpl_feat.shape
         P = prop_feat.shape[1]
         cos = torch.empty(B, O, P, device=prop_feat.device)
         if B * O * P > 0:
-            rc = lib.dmm_cosine_pairwise(_p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop), _p(n_tmpl),
-                                         float(eps), _p(cos), _stream())
+            if impl is None:
+                rc = lib.dmm_cosine_pairwise(_p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop), _p(n_tmpl),
+                                             float(eps), _p(cos), _stream())
+            else:
+                rc = lib.dmm_cosine_pairwise_impl(_p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop), _p(n_tmpl),
+                                                  float(eps), _p(cos), COSINE_IMPLS[impl], _stream())
             _lib.check(rc, "dmm_cosine_pairwise")
         ctx.save_for_backward(tmpl_feat, prop_feat, n_prop, n_tmpl, cos)
         ctx.eps = eps
@@ -283,18 +287,23 @@ class _CosineFn(torch.autograd.Function):
             rc = lib.dmm_cosine_pairwise_bwd(_p(g_cos), _p(cos), _p(tmpl_feat), _p(prop_feat), B, T, P, O, D, _p(n_prop),
                                              _p(n_tmpl), float(ctx.eps), _p(gq), _p(gk), _stream())
             _lib.check(rc, "dmm_cosine_pairwise_bwd")
-        return gq, gk, None, None, None
+        return gq, gk, None, None, None, None
 
 
-def cosine_pairwise(tmpl_feat: torch.Tensor, prop_feat: torch.Tensor, n_prop=None, n_tmpl=None, eps: float = 1e-8):
-    """tmpl_feat [B,T,O,D] (T template-feature sets), prop_feat [B,P,D] -> mean_t cos [B,O,P]; differentiable."""
+COSINE_IMPLS = {"auto": 0, "simt": 1, "tc": 2}
+
+
+def cosine_pairwise(tmpl_feat: torch.Tensor, prop_feat: torch.Tensor, n_prop=None, n_tmpl=None, eps: float = 1e-8,
+                    impl: Optional[str] = None):
+    """tmpl_feat [B,T,O,D] (T template-feature sets), prop_feat [B,P,D] -> mean_t cos [B,O,P]; differentiable.
+    ``impl``: None (library default: the tcgen05 3xTF32 kernel inside its envelope, else fp32 FFMA), "tc", "simt"."""
     tmpl_feat = _cuda_f32(tmpl_feat, "tmpl_feat")
     prop_feat = _cuda_f32(prop_feat, "prop_feat")
     B = prop_feat.shape[0]
     assert tmpl_feat.dim() == 4 and prop_feat.dim() == 3 and tmpl_feat.shape[0] == B
     assert tmpl_feat.shape[3] == prop_feat.shape[2], (tmpl_feat.shape, prop_feat.shape)
     return _CosineFn.apply(tmpl_feat, prop_feat, _counts(n_prop, B, prop_feat.device),
-                           _counts(n_tmpl, B, prop_feat.device), eps)
+                           _counts(n_tmpl, B, prop_feat.device), eps, impl)
 
 
 # ----------------------------------------------------------------------------------------------------------

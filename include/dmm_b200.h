@@ -101,6 +101,14 @@ int dmm_mask_iou_rowwise(const float* a, const float* b, int N, int M, float* io
  */
 int dmm_cosine_pairwise(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
                         const int* n_prop, const int* n_tmpl, float eps, float* cos, void* stream);
+/* Same with an explicit kernel choice.  DMM_COSINE_TC: the contraction runs on the tensor cores (tcgen05.mma kind::tf32
+ * as a 3xTF32 split with fp32 accumulation in TMEM, features streamed by TMA; |err| ~3e-6 of an fp64 reference);
+ * envelope T == 1, P <= 64, O <= 16, D >= 32, D % 4 == 0, 16-byte aligned features, else DMM_ERR_UNSUPPORTED_SHAPE.
+ * DMM_COSINE_SIMT: fp32 FFMA kernel, any shape (|err| ~3e-7).  DMM_COSINE_AUTO (what dmm_cosine_pairwise does): TC
+ * inside the envelope, SIMT outside; the environment variable DMM_K2_IMPL=simt forces SIMT for dmm_cosine_pairwise. */
+enum { DMM_COSINE_AUTO = 0, DMM_COSINE_SIMT = 1, DMM_COSINE_TC = 2 };
+int dmm_cosine_pairwise_impl(const float* tmpl_feat, const float* prop_feat, int B, int T, int P, int O, int D,
+                             const int* n_prop, const int* n_tmpl, float eps, float* cos, int impl, void* stream);
 /* d(loss)/d(features) from g_cos [B][O][P]; g_tmpl_feat [B][T][O][D], g_prop_feat [B][P][D] are overwritten.
  * cos_fwd (optional, may be NULL): the forward's output; used instead of recomputing the cosines when T == 1. */
 int dmm_cosine_pairwise_bwd(const float* g_cos, const float* cos_fwd, const float* tmpl_feat, const float* prop_feat,

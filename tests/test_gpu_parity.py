@@ -74,7 +74,7 @@ def test_layer_against_reference_golden(name):
 
     iou = ops.mask_iou_pairwise(pm[None], tm[None])["iou"][0]
     np.testing.assert_array_equal(iou.cpu().numpy(), g["iou"])                      # bit-exact vs the reference
-    close(match_helper.get_cosine_score(tf, pf), g["cos"], 2e-6, "cos")
+    close(match_helper.get_cosine_score(tf, pf), g["cos"], 5e-6, "cos")              # tcgen05 3xTF32: ~3e-6; bar 1e-4
     with torch.no_grad():
         L = int(layer.forward_many(pf[None], pm[None], tf[None], tm[None], sc[None])["n_list"][0])
     L_ref = int(g["n_list"])
@@ -84,7 +84,7 @@ def test_layer_against_reference_golden(name):
         sim, n_prop, n_tplt, _ = layer.compute_cost_matrix({"proposed": pf, "template": [tf]},
                                                            {"proposed": pm, "template": tm}, {"proposal_score": sc}, tg)
         assert (n_prop, n_tplt) == (P, O)
-        close(sim, g["sim"], 2e-6, "sim")
+        close(sim, g["sim"], 5e-6, "sim")
         _, _, _, logic, bmat = layer.match_with_first_frame(sim, P, O, pm, sc, tm)
         close(bmat, want["bmat"], TOL, "bmat")
         np.testing.assert_array_equal(logic.cpu().numpy(), want["logic"])            # same selected entries
