@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if src.endswith(".cpp"):   # host-only code (mask packing): host compiler flags, OpenMP
             cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "-c", os.path.join(CSRC, src), "-o", obj]
         else:
-            cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+            extra = os.environ.get("DMM_BUILD_DEFINES", "").split()          # e.g. -DDMM_K2_TRACE (debug builds only)
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, pr in procs:
         out, _ = pr.communicate()

@@ -5,7 +5,7 @@
 // (cosine.cu): cos[b,o,p] = <q_o,k_p> / (max(|q_o|,eps) * max(|k_p|,eps)), 0 for padding rows / columns.
 //
 // Why a tensor-core kernel for 0.5 MFLOP per match: the SIMT kernel is latency-bound (100 ns per match, 1.2 TB/s);
-// with the contraction on tcgen05 the kernel is a pure TMA stream of the (P+O)*D*4 = 122 880 feature bytes per match.
+// with the contraction on tcgen05 the kernel is a TMA stream of the (P+O)*D*4 = 122 880 feature bytes per match.
 // Parity needs fp32-grade dot products, so the contraction is 3xTF32: every fp32 operand is split on chip into
 // hi = x & 0xffffe000 (exactly a TF32 number) and lo = tf32(x - hi); D += lo*hi + hi*lo + hi*hi leaves a relative error
 // of ~2^-21 per product (the dropped lo*lo term) with fp32 accumulation in TMEM.
@@ -14,23 +14,31 @@
 // (rows 0-63 / 64-127 = proposals of the two problems, columns 0-15 / 16-31 = their templates; only the two diagonal
 // 64 x 16 blocks are read back).  Per 32-float K chunk (one 128-byte swizzle row):
 //   warp 10  (1 lane)  TMA: four cp.async.bulk.tensor.2d boxes (SWIZZLE_128B) land the fp32 chunk of both problems'
-//                      proposals [64 x 32] and templates [16 x 32] in a ring slot, already in the K-major canonical layout;
-//   warps 0-9          split pass: two threads per operand row (64 bytes each); LDS.128 (conflict-free thanks to the
-//                      swizzle) -> hi in place, lo into a slot of the 2-deep lo ring, sum of squares of the half row in a
-//                      register (the norms ride along for free); fence.proxy.async + mbarrier arrive;
-//   warp 11  (1 lane)  12 x tcgen05.mma.kind::tf32 M128 N32 K8 (4 K steps x {lo*hi, hi*lo, hi*hi}), tcgen05.commit
-//                      frees the stage / publishes the accumulator;
+//                      proposals [64 x 32] and templates [16 x 32] in a slot of the 8-deep raw ring;
+//   warps 0-7          split pass for the proposals (the M operand): thread = one row; LDS.128 (conflict-free thanks to
+//                      the swizzle) -> hi / lo go to TENSOR MEMORY with tcgen05.st (row = TMEM lane, K element = column),
+//                      the sum of squares of the row stays in a register (the norms ride along for free);
+//   warps 8-9          split pass for the templates (the N operand): hi / lo into a small shared-memory operand ring in
+//                      the K-major SWIZZLE_128B canonical layout, fence.proxy.async;
+//                      (warps 0-3 + 8 take the even chunks, warps 4-7 + 9 the odd ones)
+//   warp 11  (1 lane)  12 x tcgen05.mma.kind::tf32 M128 N32 K8, A from TMEM, B from shared memory (4 K steps x
+//                      {lo*hi, hi*lo, hi*hi}); tcgen05.commit frees the operand slot / publishes the accumulator;
 //   warps 12-15        epilogue: tcgen05.ld 32x32b.x16 of the own problem's 16 columns, divide by the norms, coalesced
 //                      stores of cos[b][o][p].  Two accumulator buffers decouple it from the next pair.
+// Why A lives in TMEM: with both operands in shared memory the kernel was SHARED-MEMORY-BANDWIDTH bound -- every K8 MMA
+// re-reads its whole 128-row A slice, 60 KB of operand fetches per chunk on top of 60 KB of split-pass traffic and the
+// 20 KB the TMA writes (measured 0.74 us per chunk; 0.38 us with the MMAs removed).  A in TMEM takes the operand
+// fetches of the big operand off the shared-memory port.
 // The tensor core's fp32 accumulation truncates when it aligns addends (measured: one accumulator over all 64 K steps
 // leaves 1e-5 on cos; the error grows with the number of chained MMAs), so K is cut into 4 groups that accumulate in
-// separate TMEM columns and are added with round-to-nearest fp32 in the epilogue.
-// The raw/hi ring is 8 slots deep (160 KB in flight per SM): with 4 slots the kernel ran at the pace of the
-// TMA -> split -> MMA -> commit round trip (0.7 us per chunk measured, 3.2 TB/s).
+// separate TMEM columns and are added with round-to-nearest fp32 in the epilogue (measured 3e-6).
+// TMEM map (512 columns): [0,256) two accumulator buffers x 4 K groups x 32 columns; [256,512) four operand slots x
+// (32 columns hi + 32 columns lo).
 // Rows 50..63 of a box are the next problem's first proposals (2-D tensor map over [B*P][D]); they only ever feed
 // accumulator rows nobody reads.  The TMA zero-fills past the end of the tensor and past D.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -39,23 +47,34 @@
 namespace dmm {
 namespace {
 
-constexpr int kStages = 6;                      // raw fp32 / hi ring: what the TMA keeps in flight (8 x 20 KB per SM)
-constexpr int kLoStages = 4;                    // lo ring: lives only from the split pass to the MMAs that read it
+constexpr int kStages = 8;                      // raw fp32 ring: what the TMA keeps in flight (8 x 20 KB per SM)
+constexpr int kOpStages = 4;                    // operand ring: A hi/lo in TMEM, B hi/lo in shared memory
 constexpr int kKC = 32;                         // floats per K chunk (128-byte swizzle row)
 constexpr int kRowsA = 128, kRowsB = 32;        // accumulator M (2 x 64 proposals), N (2 x 16 templates)
 constexpr int kPadP = 64, kPadO = 16;
 constexpr uint32_t kBytesA = kRowsA * kKC * 4;  // 16 KB
 constexpr uint32_t kBytesB = kRowsB * kKC * 4;  // 4 KB
-constexpr uint32_t kStageBytes = kBytesA + kBytesB;           // one ring slot (both operands): 20 KB
-constexpr int kConvWarps = 10, kConvThreads = kConvWarps * 32;   // two threads per operand row (64 bytes each)
-constexpr int kTmaWarp = 10, kMmaWarp = 11, kEpiWarp0 = 12;       // epilogue warps 12-15: warp % 4 = TMEM lane quarter
+constexpr uint32_t kStageBytes = kBytesA + kBytesB;           // raw slot (both operands): 20 KB
+constexpr uint32_t kOpBytes = 2 * kBytesB;                    // B hi + lo: 8 KB
+constexpr int kConvWarps = 10;                                // two groups of (4 proposal warps + 1 template warp)
+constexpr int kGroupWarps = kConvWarps / 2;
+constexpr int kTmaWarp = 10, kMmaWarp = 11, kEpiWarp0 = 12;   // epilogue warps 12-15: warp % 4 = TMEM lane quarter
 constexpr int kThreadsTc = 16 * 32;
-constexpr size_t kDynSmem = (size_t)(kStages + kLoStages) * kStageBytes + 1024;   // 201 KB
-constexpr int kGroups = 4;                                        // K is accumulated in 4 separate TMEM accumulators ...
-constexpr uint32_t kAccCols = kGroups * kRowsB;                   // ... of 32 columns each, summed in fp32 by the epilogue
-constexpr uint32_t kTmemCols = 2 * kAccCols;                      // double-buffered: 256 columns
+constexpr size_t kDynSmem = (size_t)kStages * kStageBytes + (size_t)kOpStages * kOpBytes + 1024;   // 193 KB
+constexpr int kGroups = 4;                                    // K is accumulated in 4 separate TMEM accumulators ...
+constexpr uint32_t kAccCols = kGroups * kRowsB;               // ... of 32 columns each, summed in fp32 by the epilogue
+constexpr uint32_t kOpCol0 = 2 * kAccCols;                    // first TMEM column of the A operand ring
+constexpr uint32_t kOpCols = 2 * kKC;                         // hi + lo columns per slot
+constexpr uint32_t kTmemCols = 512;
+
+#ifdef DMM_K2_TRACE   // debug build only: per-chunk clock64 stamps of CTA 0 (scripts/prof_k2.py --trace)
+#define K2_STAMP(slot, g) do { if (blockIdx.x == 0 && (g) < 128 && p.trace && (threadIdx.x & 31) == 0) p.trace[(slot) * 128 + (g)] = clock64(); } while (0)
+#else
+#define K2_STAMP(slot, g) do { } while (0)
+#endif
 
 struct TcParams {
+  long long* trace;
   int B, P, O, D, pairs, nK, per_group;
   const int* n_prop;
   const int* n_tmpl;
@@ -97,20 +116,42 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+// One lane of a converged warp (elect.sync).  Issuing tcgen05.mma / cp.async.bulk.tensor under `if (lane == 0)` makes the
+// compiler wrap EVERY such instruction in an ELECT / BRA.U.ANY convergence loop (measured: 75 cycles per MMA, the MMA
+// warp became the bottleneck of the whole kernel); under elect.sync it emits them back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 
@@ -130,27 +171,29 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRo
 __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_k,
                                                                   const __grid_constant__ CUtensorMap map_q) {
   extern __shared__ uint8_t dyn_raw[];
-  __shared__ uint64_t full_bar[kStages], conv_bar[kStages], empty_bar[kStages], lo_empty[kLoStages];
+  __shared__ uint64_t raw_full[kStages], raw_empty[kStages], op_full[kOpStages], op_empty[kOpStages];
   __shared__ uint64_t tmem_full[2], tmem_empty[2], norm_full[2];
-  __shared__ float s_knorm2[2][2][kRowsA], s_qnorm2[2][2][kRowsB];   // [buffer][row half]: partial sums of squares
+  __shared__ float s_knorm2[2][2][kRowsA], s_qnorm2[2][2][kRowsB];   // [buffer][converter group]: partial sums of squares
   __shared__ uint32_t s_tmem_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t stage0 = (smem_u32(dyn_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024-byte alignment
-  const uint32_t lo0 = stage0 + kStages * kStageBytes;
-  uint8_t* const smem_gen = dyn_raw;                                 // generic pointer / shared address of the same byte
   const uint32_t smem_base = smem_u32(dyn_raw);
+  uint8_t* const smem_gen = dyn_raw;                                 // generic pointer / shared address of the same byte
+  const uint32_t stage0 = (smem_base + 1023u) & ~1023u;              // swizzle atoms need 1024-byte alignment
+  const uint32_t op0 = stage0 + kStages * kStageBytes;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&conv_bar[s]), kConvWarps);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&raw_full[s]), 1);
+      mbar_init(smem_u32(&raw_empty[s]), kGroupWarps);
     }
-    for (int l = 0; l < kLoStages; ++l) mbar_init(smem_u32(&lo_empty[l]), 1);
+    for (int l = 0; l < kOpStages; ++l) {
+      mbar_init(smem_u32(&op_full[l]), kGroupWarps);
+      mbar_init(smem_u32(&op_empty[l]), 1);
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
       mbar_init(smem_u32(&tmem_empty[a]), 128);
-      mbar_init(smem_u32(&norm_full[a]), kConvThreads);
+      mbar_init(smem_u32(&norm_full[a]), kConvWarps * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -166,34 +209,38 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
   const int my_pairs = p.pairs > (int)blockIdx.x ? (p.pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == kTmaWarp) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int it = 0; it < my_pairs; ++it) {
-        const int pair = blockIdx.x + it * gridDim.x;
-        const int b0 = 2 * pair;
-        const bool two = b0 + 1 < p.B;
-        for (int kc = 0; kc < p.nK; ++kc, ++g) {
-          const uint32_t s = g % kStages;
-          if (g >= kStages) mbar_wait(smem_u32(&empty_bar[s]), ((g / kStages) - 1u) & 1u);
-          const uint32_t bar = smem_u32(&full_bar[s]);
-          const uint32_t a_hi = stage0 + s * kStageBytes, b_hi = a_hi + kBytesA;
+    // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    uint32_t g = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int pair = blockIdx.x + it * gridDim.x;
+      const int b0 = 2 * pair;
+      const bool two = b0 + 1 < p.B;
+      for (int kc = 0; kc < p.nK; ++kc, ++g) {
+        const uint32_t s = g % kStages;
+        if (g >= kStages) mbar_wait(smem_u32(&raw_empty[s]), ((g / kStages) - 1u) & 1u);
+        K2_STAMP(0, g);
+        const uint32_t bar = smem_u32(&raw_full[s]);
+        const uint32_t a_raw = stage0 + s * kStageBytes, b_raw = a_raw + kBytesA;
+        if (elect_one()) {
           mbar_expect_tx(bar, (two ? 2u : 1u) * (kBytesA / 2 + kBytesB / 2));
-          tma_load_2d(a_hi, &map_k, kc * kKC, b0 * p.P, bar);
-          tma_load_2d(b_hi, &map_q, kc * kKC, b0 * p.O, bar);
+          tma_load_2d(a_raw, &map_k, kc * kKC, b0 * p.P, bar);
+          tma_load_2d(b_raw, &map_q, kc * kKC, b0 * p.O, bar);
           if (two) {
-            tma_load_2d(a_hi + kBytesA / 2, &map_k, kc * kKC, (b0 + 1) * p.P, bar);
-            tma_load_2d(b_hi + kBytesB / 2, &map_q, kc * kKC, (b0 + 1) * p.O, bar);
+            tma_load_2d(a_raw + kBytesA / 2, &map_k, kc * kKC, (b0 + 1) * p.P, bar);
+            tma_load_2d(b_raw + kBytesB / 2, &map_q, kc * kKC, (b0 + 1) * p.O, bar);
           }
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp < kConvWarps) {
     // ===== split pass: fp32 -> (hi, lo) TF32 pair, row norms =====
+    // Two groups of (4 proposal warps + 1 template warp) take alternate chunks: a thread's per-chunk latency is mostly
+    // synchronisation (two mbarrier waits, tcgen05.wait::st, fences: ~900 cycles measured against ~300 of work for a
+    // whole 128-byte row), so two chunks are in flight in the split pass at any time.
     const bool is_a = warp < 8;
-    const int half = is_a ? (tid >> 7) : ((tid - 256) >> 5);   // which 64 bytes of the 128-byte row
-    const int row = is_a ? (tid & 127) : lane;                 // operand row owned by this thread
+    const uint32_t grp = is_a ? (uint32_t)(warp >> 2) : (uint32_t)(warp - 8);
+    const int row = is_a ? ((warp & 3) * 32 + lane) : lane;    // operand row; for A also the TMEM lane this warp may write
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
     uint32_t g = 0;
@@ -201,77 +248,106 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
       const int ab = it & 1;
       float nrm = 0.f;
       for (int kc = 0; kc < p.nK; ++kc, ++g) {
-        const uint32_t s = g % kStages, l = g % kLoStages;
-        mbar_wait(smem_u32(&full_bar[s]), (g / kStages) & 1u);
-        if (g >= kLoStages) mbar_wait(smem_u32(&lo_empty[l]), ((g / kLoStages) - 1u) & 1u);
-        const uint32_t hi_base = stage0 + s * kStageBytes + (is_a ? 0u : kBytesA) + row_off;
-        const uint32_t lo_base = lo0 + l * kStageBytes + (is_a ? 0u : kBytesA) + row_off;
-        // all four 16-byte loads first (independent), then the arithmetic, then the eight stores: the thread's chunk
-        // latency is the pipeline's period (every converter works on the same chunk), so the loads must overlap
-        uint4 x[4];
-        uint32_t off[4];
+        if ((g & 1u) != grp) continue;
+        const uint32_t s = g % kStages, l = g % kOpStages;
+        mbar_wait(smem_u32(&raw_full[s]), (g / kStages) & 1u);
+        if (tid == 0) K2_STAMP(1, g);
+        if (tid == 256) K2_STAMP(5, g);
+        const uint32_t raw = stage0 + s * kStageBytes + (is_a ? 0u : kBytesA) + row_off;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kOpCol0 + l * kOpCols;
+        const uint32_t ob = op0 + l * kOpBytes + row_off;
+        uint4 x[8];                                          // the whole 128-byte row: eight independent loads first
 #pragma unroll
-        for (uint32_t c4 = 0; c4 < 4; ++c4) {
-          off[c4] = (((uint32_t)half * 4u + c4) ^ sw) << 4;
-          x[c4] = *reinterpret_cast<const uint4*>(smem_gen + (hi_base + off[c4] - smem_base));
+        for (uint32_t c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const uint4*>(smem_gen + (raw + ((c ^ sw) << 4) - smem_base));
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+          nrm = fmaf(__uint_as_float(x[c].x), __uint_as_float(x[c].x), nrm);
+          nrm = fmaf(__uint_as_float(x[c].y), __uint_as_float(x[c].y), nrm);
+          nrm = fmaf(__uint_as_float(x[c].z), __uint_as_float(x[c].z), nrm);
+          nrm = fmaf(__uint_as_float(x[c].w), __uint_as_float(x[c].w), nrm);
         }
-        {
+        if (g >= kOpStages) mbar_wait(smem_u32(&op_empty[l]), ((g / kOpStages) - 1u) & 1u);   // MMAs of chunk g-4 done
+        if (tid == 0) K2_STAMP(2, g);
+        if (is_a) tc_fence_after();
+#pragma unroll
+        for (uint32_t h = 0; h < 2; ++h) {                   // 16 K elements at a time keeps the register count down
+          uint32_t hi[16], lo[16];
 #pragma unroll
           for (uint32_t c4 = 0; c4 < 4; ++c4) {
-            const float f0 = __uint_as_float(x[c4].x), f1 = __uint_as_float(x[c4].y), f2 = __uint_as_float(x[c4].z),
-                        f3 = __uint_as_float(x[c4].w);
-            nrm = fmaf(f0, f0, nrm); nrm = fmaf(f1, f1, nrm); nrm = fmaf(f2, f2, nrm); nrm = fmaf(f3, f3, nrm);
-            uint4 h, l;
-            h.x = x[c4].x & 0xffffe000u; h.y = x[c4].y & 0xffffe000u; h.z = x[c4].z & 0xffffe000u; h.w = x[c4].w & 0xffffe000u;
-            l.x = __float_as_uint(__fsub_rn(f0, __uint_as_float(h.x))) & 0xffffe000u;
-            l.y = __float_as_uint(__fsub_rn(f1, __uint_as_float(h.y))) & 0xffffe000u;
-            l.z = __float_as_uint(__fsub_rn(f2, __uint_as_float(h.z))) & 0xffffe000u;
-            l.w = __float_as_uint(__fsub_rn(f3, __uint_as_float(h.w))) & 0xffffe000u;
-            *reinterpret_cast<uint4*>(smem_gen + (hi_base + off[c4] - smem_base)) = h;
-            *reinterpret_cast<uint4*>(smem_gen + (lo_base + off[c4] - smem_base)) = l;
+            const uint4 v = x[4 * h + c4];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[4 * c4 + e] = w[e] & 0xffffe000u;
+              lo[4 * c4 + e] = __float_as_uint(__fsub_rn(__uint_as_float(w[e]), __uint_as_float(hi[4 * c4 + e]))) & 0xffffe000u;
+            }
+          }
+          if (is_a) {
+            tmem_st16(taddr + 16u * h, hi);
+            tmem_st16(taddr + kKC + 16u * h, lo);
+          } else {
+#pragma unroll
+            for (uint32_t c4 = 0; c4 < 4; ++c4) {
+              const uint32_t off = ((4 * h + c4) ^ sw) << 4;
+              *reinterpret_cast<uint4*>(smem_gen + (ob + off - smem_base)) =
+                  make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
+              *reinterpret_cast<uint4*>(smem_gen + (ob + kBytesB + off - smem_base)) =
+                  make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
+            }
           }
         }
-        fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core's async proxy
+        if (is_a) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        } else {
+          fence_proxy_async();                                // generic-proxy stores -> visible to the tensor core's async proxy
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&conv_bar[s]));   // one arrival per warp: 320 per-thread arrivals on one
-                                                              // mbarrier serialised the whole chunk (measured 1 us / chunk)
+        if (lane == 0) {                                      // one arrival per warp (per-thread arrivals serialise on the barrier)
+          mbar_arrive(smem_u32(&raw_empty[s]));               // raw slot consumed (values are in registers / operand ring)
+          mbar_arrive(smem_u32(&op_full[l]));
+          if (tid == 0) K2_STAMP(3, g);
+          if (tid == 256) K2_STAMP(6, g);
+        }
       }
       // hand the partial sum of squares to the epilogue (buffer `ab` is free once the epilogue of pair it-2 has arrived)
       if (it >= 2) mbar_wait(smem_u32(&tmem_empty[ab]), ((it >> 1) - 1) & 1);
-      if (is_a) s_knorm2[ab][half][row] = nrm; else s_qnorm2[ab][half][row] = nrm;
+      if (is_a) s_knorm2[ab][grp][row] = nrm; else s_qnorm2[ab][grp][row] = nrm;
       mbar_arrive(smem_u32(&norm_full[ab]));
     }
   } else if (warp == kMmaWarp) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int it = 0; it < my_pairs; ++it) {
-        const int ab = it & 1;
-        if (it >= 2) mbar_wait(smem_u32(&tmem_empty[ab]), ((it >> 1) - 1) & 1);
+    // ===== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+    uint32_t g = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int ab = it & 1;
+      if (it >= 2) mbar_wait(smem_u32(&tmem_empty[ab]), ((it >> 1) - 1) & 1);
+      tc_fence_after();
+      int grp = 0, in_grp = 0;                               // K group -> its own 32 accumulator columns
+      for (int kc = 0; kc < p.nK; ++kc, ++g) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)ab * kAccCols + (uint32_t)grp * kRowsB;
+        const bool first = in_grp == 0;
+        if (++in_grp == p.per_group) { in_grp = 0; ++grp; }
+        const uint32_t l = g % kOpStages;
+        mbar_wait(smem_u32(&op_full[l]), (g / kOpStages) & 1u);
+        K2_STAMP(4, g);
         tc_fence_after();
-        for (int kc = 0; kc < p.nK; ++kc, ++g) {
-          const int grp = kc / p.per_group;                    // K group -> its own 32 accumulator columns
-          const uint32_t d_tmem = tmem_base + (uint32_t)ab * kAccCols + (uint32_t)grp * kRowsB;
-          const bool first = kc == grp * p.per_group;
-          const uint32_t s = g % kStages, l = g % kLoStages;
-          mbar_wait(smem_u32(&conv_bar[s]), (g / kStages) & 1u);
-          tc_fence_after();
-          const uint32_t a_hi = stage0 + s * kStageBytes, b_hi = a_hi + kBytesA;
-          const uint32_t a_lo = lo0 + l * kStageBytes, b_lo = a_lo + kBytesA;
-          const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_lo), db_hi = umma_desc(b_hi), db_lo = umma_desc(b_lo);
+        const uint32_t a_hi = tmem_base + kOpCol0 + l * kOpCols, a_lo = a_hi + kKC;
+        const uint32_t b_hi = op0 + l * kOpBytes, b_lo = b_hi + kBytesB;
+        const uint64_t db_hi = umma_desc(b_hi), db_lo = umma_desc(b_lo);
+        if (elect_one()) {
 #pragma unroll
-          for (uint32_t k = 0; k < kKC / 8; ++k) {           // 8 TF32 per MMA = 32 bytes = 2 descriptor address units
-            tc_mma_tf32(d_tmem, da_lo + 2 * k, db_hi + 2 * k, kIdesc, !(first && k == 0));
-            tc_mma_tf32(d_tmem, da_hi + 2 * k, db_lo + 2 * k, kIdesc, 1u);
-            tc_mma_tf32(d_tmem, da_hi + 2 * k, db_hi + 2 * k, kIdesc, 1u);
+          for (uint32_t k = 0; k < kKC / 8; ++k) {           // 8 TF32 per MMA: 8 TMEM columns of A, 32 bytes (2 address units) of B
+            tc_mma_tf32_ts(d_tmem, a_lo + 8 * k, db_hi + 2 * k, kIdesc, !(first && k == 0));
+            tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, db_lo + 2 * k, kIdesc, 1u);
+            tc_mma_tf32_ts(d_tmem, a_hi + 8 * k, db_hi + 2 * k, kIdesc, 1u);
           }
-          tc_commit(smem_u32(&empty_bar[s]));                 // ring slots reusable once these MMAs have read them
-          tc_commit(smem_u32(&lo_empty[l]));
+          tc_commit(smem_u32(&op_empty[l]));                  // operand slot reusable once these MMAs have read it
+          if (kc == p.nK - 1) tc_commit(smem_u32(&tmem_full[ab]));   // accumulator complete
         }
-        tc_commit(smem_u32(&tmem_full[ab]));                  // accumulator complete
+        __syncwarp();
+        K2_STAMP(7, g);
       }
     }
-    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue =====
     const int q4 = warp & 3;                                  // TMEM lane quarter this warp may read
@@ -372,10 +448,33 @@ int cosine_tc_try_launch(const float* tmpl_feat, const float* prop_feat, int B, 
   kp.B = B; kp.P = P; kp.O = O; kp.D = D; kp.pairs = (B + 1) / 2; kp.nK = (D + kKC - 1) / kKC;
   kp.per_group = (kp.nK + kGroups - 1) / kGroups;
   kp.n_prop = n_prop; kp.n_tmpl = n_tmpl; kp.eps = eps; kp.cos = cos;
+  kp.trace = nullptr;
+#ifdef DMM_K2_TRACE
+  static long long* trace_buf = nullptr;
+  if (getenv("DMM_K2_TRACE_FILE")) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 8 * 128 * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 8 * 128 * sizeof(long long), st);
+    kp.trace = trace_buf;
+  }
+#endif
   cudaError_t e = cudaFuncSetAttribute(cosine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
   if (e != cudaSuccess) { set_last_cuda_error((int)e); return DMM_ERR_CUDA; }
   const int grid = kp.pairs < kNumSMs ? kp.pairs : kNumSMs;
   cosine_tc_kernel<<<grid, kThreadsTc, kDynSmem, st>>>(kp, mk, mq);
+#ifdef DMM_K2_TRACE
+  if (kp.trace) {
+    static long long host[8 * 128];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, kp.trace, sizeof(host), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("DMM_K2_TRACE_FILE"), "w")) {
+      for (int g = 0; g < 128; ++g) {
+        for (int sl = 0; sl < 8; ++sl) fprintf(f, "%lld ", host[sl * 128 + g]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+#endif
   return check_launch();
 }
 
