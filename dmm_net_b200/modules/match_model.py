@@ -58,14 +58,15 @@ class MatchModel(nn.Module):
                                n_tmpl=n_tmpl, row_map=row_map, O_out=out_rows)
 
     def forward_many_host(self, proposed_feature, proposed_mask, template_feature, mask_last_occurence, proposal_score,
-                          device="cuda", threads=None, n_prop=None, n_tmpl=None):
-        """cost-build + solve for inputs held in HOST memory (CPU fp32 tensors): the host cores bit-pack the masks, only
-        bits + features + scores cross PCIe (``ops.match_batch_host``).  Returns device tensors (sim, R, Bmat, scores...)."""
+                          device="cuda", threads=None, n_prop=None, n_tmpl=None, raw_fraction=None):
+        """cost-build + solve for inputs held in HOST memory (CPU fp32 tensors): the host cores bit-pack most masks (only
+        bits cross PCIe) while the copy engine DMAs the rest as fp32 (``ops.match_batch_host``).  Returns device tensors
+        (sim, R, Bmat, scores...)."""
         assert self.match_algo == 'relax'
         return ops.match_batch_host(proposed_feature, proposed_mask, template_feature, mask_last_occurence, proposal_score,
                                     max_iter=self.max_iter, proj_iter=self.proj_iter, lr=self.relax_lr,
                                     score_weight=self.cfgs['score_weight'], is_test=bool(self.is_test), device=device,
-                                    threads=threads, n_prop=n_prop, n_tmpl=n_tmpl)
+                                    threads=threads, n_prop=n_prop, n_tmpl=n_tmpl, raw_fraction=raw_fraction)
 
     # ------------------------------------------------------------------------------------------------------
     def compute_cost_matrix(self, features, mask, scores, targets=None):

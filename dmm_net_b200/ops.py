@@ -875,16 +875,27 @@ def _pinned(key, shape, dtype):
     return t
 
 
+_HOST_SPLIT = {}          # (P, O, HW) -> running estimate of seconds per problem for the two routes (pack, dma)
+
+
 def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, max_iter: int, proj_iter: int, lr: float,
                      score_weight: float, is_test: bool, device="cuda", threads: Optional[int] = None, n_prop=None,
-                     n_tmpl=None):
+                     n_tmpl=None, raw_fraction: Optional[float] = None):
     """cost-build + solve for a batch whose inputs live in HOST memory (CPU fp32 tensors, pinned or not).
 
-    The IoU needs only the thresholded bits, so the host cores pack the masks (OpenMP + AVX2, memory speed) and only
-    bits + features + scores cross PCIe: 0.98 MB instead of 27.65 MB per match at the headline size.  Device side:
-    K2 cosine -> K1 on packed rows (+finalize/mix) -> K3 solver+head.  Returns the dict of ``cost_and_solve`` (device
-    tensors; ``iou``/``sim`` are bit-identical to the fp32-mask path).  The soft masks stay on the host: the
-    assignment-apply (which needs <= O selected rows per problem) is left to the caller / ``match_batch``."""
+    Two routes feed the device at the same time:
+    * **packed**: the IoU needs only the thresholded bits, so the host cores pack the masks (OpenMP + AVX2, memory speed)
+      and only bits cross PCIe: 0.86 MB instead of 27.5 MB of masks per match at the headline size (K1 on packed rows);
+    * **raw**: while the cores are packing, the copy engine -- otherwise idle -- DMAs the fp32 masks of the first
+      ``raw_fraction`` of the problems straight from pinned memory (K1 on fp32 rows, the TMA kernel).
+    The split is chosen so that both routes finish together: ``raw_fraction=None`` tracks the measured seconds per problem
+    of each route (host wall clock for the packing, CUDA events for the DMA) across calls; 0 disables the raw route
+    (also when the masks are not pinned: the copy would not be asynchronous).  Both routes produce the same integer
+    counts, so ``iou`` / ``sim`` are bit-identical whichever route a problem takes.
+    Device side: K2 cosine -> K1 (fp32 rows | packed rows, +finalize/mix) -> K3 solver+head.  Returns the dict of
+    ``cost_and_solve`` (device tensors).  The soft masks stay on the host: the assignment-apply (which needs <= O selected
+    rows per problem) is left to the caller / ``match_batch``."""
+    import time
     lib = _lib.load()
     for t in (prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score):
         assert not t.is_cuda and t.dtype == torch.float32, "match_batch_host takes CPU fp32 tensors"
@@ -898,20 +909,77 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
         HW *= int(dsz)
     words = packed_words(HW)
     th = host_threads() if threads is None else int(threads)
-    pb = pack_masks_host(prop_mask.reshape(B, P, HW), mask_dims=1, threads=th, out=_pinned("pb", (B, P, words), torch.int32))
-    tb = pack_masks_host(tmpl_mask.reshape(B, O, HW), mask_dims=1, threads=th, out=_pinned("tb", (B, O, words), torch.int32))
+    prop_mask = prop_mask.reshape(B, P, HW)
+    tmpl_mask = tmpl_mask.reshape(B, O, HW)
+    key = (P, O, HW)
+    can_raw = prop_mask.is_pinned() and tmpl_mask.is_pinned() and prop_mask.is_contiguous() and tmpl_mask.is_contiguous()
+    if raw_fraction is None:
+        est = _HOST_SPLIT.get(key)
+        # first call: nominal 100 GB/s of packing against 50 GB/s of PCIe; afterwards the best rates measured so far
+        t_pack, t_dma = est if est else (1.0, 2.0)
+        raw_fraction = min(0.6, t_pack / (t_pack + t_dma))
+    nraw = int(round(B * float(raw_fraction))) if can_raw and B >= 4 else 0
+    nraw = max(0, min(nraw, B))
+    main = torch.cuda.current_stream(dev)
     to_dev = lambda t: t.to(dev, non_blocking=True)
-    pbd, tbd = to_dev(pb), to_dev(tb)
+    pm_raw = tm_raw = None
+    ev_dma = None
+    if nraw > 0:
+        copy_stream = _side_streams(dev)[0]
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pm_raw, tm_raw = to_dev(prop_mask[:nraw]), to_dev(tmpl_mask[:nraw])
+            ev_dma = torch.cuda.Event(enable_timing=True)
+            ev_dma.record()
+    npk = B - nraw
+    t_host = 0.0
+    if npk > 0:
+        _pinned("pb", (B, P, words), torch.int32), _pinned("tb", (B, O, words), torch.int32)   # allocated outside the timing
+        t0 = time.perf_counter()
+        # staging buffers are sized for the whole batch (the split moves from call to call; re-pinning would cost more)
+        pb = pack_masks_host(prop_mask[nraw:], mask_dims=1, threads=th, out=_pinned("pb", (B, P, words), torch.int32)[:npk])
+        tb = pack_masks_host(tmpl_mask[nraw:], mask_dims=1, threads=th, out=_pinned("tb", (B, O, words), torch.int32)[:npk])
+        t_host = time.perf_counter() - t0
+        pbd, tbd = to_dev(pb), to_dev(tb)
     pf, tf, sc = to_dev(prop_feat.contiguous()), to_dev(tmpl_feat.contiguous()), to_dev(prop_score.contiguous())
     n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
+    sl = lambda t, a, b: None if t is None else t[a:b]
     with torch.no_grad():
         cos = cosine_pairwise(tf, pf, n_prop, n_tmpl)
         w = float(score_weight)
-        r = mask_iou_pairwise_packed(pbd, tbd, None, n_prop, n_tmpl, cos=cos, w_cos=1 - w, w_iou=w)
-        R, Bm, ms, ds, Xf, logic, n_list = relax_solve(r["sim"], sc, n_prop, n_tmpl, max_iter, proj_iter, lr, True, True,
+        parts = []
+        if nraw > 0:
+            main.wait_event(ev_dma)
+            pm_raw.record_stream(main)
+            tm_raw.record_stream(main)
+            parts.append(mask_iou_pairwise(pm_raw, tm_raw, None, sl(n_prop, 0, nraw), sl(n_tmpl, 0, nraw), cos=cos[:nraw],
+                                           w_cos=1 - w, w_iou=w))
+        if npk > 0:
+            parts.append(mask_iou_pairwise_packed(pbd, tbd, None, sl(n_prop, nraw, B), sl(n_tmpl, nraw, B), cos=cos[nraw:],
+                                                  w_cos=1 - w, w_iou=w))
+        if len(parts) == 1:
+            iou, sim = parts[0]["iou"], parts[0]["sim"]
+        else:
+            iou = torch.cat([q["iou"] for q in parts], 0)
+            sim = torch.cat([q["sim"] for q in parts], 0)
+        R, Bm, ms, ds, Xf, logic, n_list = relax_solve(sim, sc, n_prop, n_tmpl, max_iter, proj_iter, lr, True, True,
                                                        bool(is_test))
-    return {"cos": cos, "iou": r["iou"], "sim": r["sim"], "R": R, "Bmat": Bm, "logic": logic, "X_final": Xf,
-            "match_score": ms, "det_score": ds, "n_list": n_list,
-            "h2d_bytes": 4 * (pb.numel() + tb.numel() + prop_feat.numel() + tmpl_feat.numel() + prop_score.numel()),
-            "host_packed_bytes": 4 * (prop_mask.numel() + tmpl_mask.numel()), "host_threads": th}
-
+    if nraw > 0 and npk > 0:
+        # update the route estimates for the next call; the DMA has finished by the time K1 ran, but do not block here:
+        # query, and keep the old estimate if the event is not ready yet
+        # (rates are properties of the machine: keep the best seen, which is robust against a slow first call, and only
+        # trust a route's measurement when it carried enough problems for its fixed costs not to dominate)
+        if ev_dma.query():
+            old = _HOST_SPLIT.get(key, (float("inf"), float("inf")))
+            t_pack = min(old[0], t_host / npk) if npk >= max(4, B // 8) else old[0]
+            t_dma = min(old[1], e0.elapsed_time(ev_dma) * 1e-3 / nraw) if nraw >= max(4, B // 8) else old[1]
+            if t_pack < float("inf") and t_dma < float("inf"):
+                _HOST_SPLIT[key] = (t_pack, t_dma)
+    h2d = 4 * (prop_feat.numel() + tmpl_feat.numel() + prop_score.numel()) + 4 * npk * (P + O) * words + \
+        4 * nraw * (P + O) * HW
+    return {"cos": cos, "iou": iou, "sim": sim, "R": R, "Bmat": Bm, "logic": logic, "X_final": Xf,
+            "match_score": ms, "det_score": ds, "n_list": n_list, "h2d_bytes": h2d,
+            "host_packed_bytes": 4 * npk * (P + O) * HW, "host_threads": th, "raw_problems": nraw, "packed_problems": npk,
+            "host_pack_seconds": t_host, "route_estimate": _HOST_SPLIT.get(key)}

@@ -412,7 +412,32 @@ def test_host_buffer_entry_matches_device_path():
     torch.cuda.synchronize()
     for k in ("iou", "sim", "R", "Bmat", "match_score", "det_score", "n_list"):
         assert torch.equal(want[k], got[k]), k
-    assert got["h2d_bytes"] < 0.1 * got["host_packed_bytes"]
+    assert got["h2d_bytes"] < 0.1 * got["host_packed_bytes"] and got["raw_problems"] == 0   # pageable inputs: packed route only
+
+
+@pytest.mark.parametrize("raw_fraction", [None, 0.0, 0.4, 1.0])
+def test_host_buffer_entry_two_routes_are_bit_identical(raw_fraction):
+    """pinned inputs: part of the batch crosses PCIe as fp32 (copy engine), the rest as bits packed by the host cores;
+    whatever the split, every output equals the device path bit for bit -- ragged counts included"""
+    B, P, O, H, W, D = 9, 50, 10, 64, 112, 64
+    pr = make_problems(B, P, O, H, W, D, seed=909)
+    layer = MatchModel(default_cfg(20, 5), is_test=1)
+    d = pr.to(DEV)
+    n_prop = torch.tensor([50, 3, 50, 17, 1, 50, 44, 50, 9], dtype=torch.int32)
+    n_tmpl = torch.tensor([10, 10, 2, 5, 1, 10, 7, 10, 3], dtype=torch.int32)
+    with torch.no_grad():
+        want = layer.forward_many(d.prop_feat, d.prop_mask, d.tmpl_feat, d.tmpl_mask, d.prop_score, n_prop=n_prop.to(DEV),
+                                  n_tmpl=n_tmpl.to(DEV))
+    pin = lambda t: t.contiguous().pin_memory()
+    for _ in range(2):                                        # second call: the split follows the measured route speeds
+        got = layer.forward_many_host(pin(pr.prop_feat), pin(pr.prop_mask), pin(pr.tmpl_feat), pin(pr.tmpl_mask),
+                                      pin(pr.prop_score), threads=4, n_prop=n_prop, n_tmpl=n_tmpl, raw_fraction=raw_fraction)
+        torch.cuda.synchronize()
+        for k in ("iou", "sim", "R", "Bmat", "match_score", "det_score", "n_list"):
+            assert torch.equal(want[k], got[k]), (k, got["raw_problems"])
+        assert got["raw_problems"] + got["packed_problems"] == B
+    if raw_fraction is not None:
+        assert got["raw_problems"] == int(round(B * raw_fraction))
 
 
 def test_randomized_shapes_against_oracle():
