@@ -4,10 +4,12 @@ DMM_Model.inference, reference dmm/modules/evaluator.py:83-134): frames of a cli
 frame t are the templates of frame t+1), clips are independent and sharded over ranks (eval.py:57-59).
 
 Everything outside the matching path is synthetic here: the backbone features are random 128-channel maps at strides
-4/8/16/32 (the north-star leaves the backbone on stock torch convs), proposals are random boxes with pasted soft masks,
-and the decoder is the identity.  What runs for real is the scope of this repo: K5 ROI mean pooling of the proposals,
-and the batched DMM_Model container (K2 cosine, K1 mask-IoU through the per-video pointer table, K3 solver, K4 apply
-with the valid-row scatter) -- one launch per kernel per frame for all clips of the rank.
+4/8/16/32 (the north-star leaves the backbone on stock torch convs), proposals are random boxes with random 28x28 mask
+head outputs, and the decoder is the identity.  What runs for real is the scope of this repo, one launch per kernel per
+frame for all clips of the rank: K8 pastes every proposal mask into the image (Masker), K9 runs the per-frame NMS on
+the tight boxes (filter_results), K5 pools the proposal features, the batched DMM_Model container matches (K2 cosine on
+the tensor cores, K1 mask-IoU through the per-video pointer table, K3 solver, K4 apply with the valid-row scatter), K6
+builds the decoder's mask-input pyramid for every object and K7 merges the output masks into the label map.
 
   python examples/synthetic_clip_eval.py [--clips 8] [--frames 12] [--proposals 50] [--objects 5] [--size 256 448]
   torchrun --nproc-per-node N examples/synthetic_clip_eval.py ...      (clips sharded, no collective in the data path)
@@ -20,7 +22,10 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dmm_net_b200 import ops                                    # noqa: E402
 from dmm_net_b200.modules.dmm_model import DMM_Model            # noqa: E402
+from dmm_net_b200.utils.boxlist_ops import filter_results      # noqa: E402
+from dmm_net_b200.utils.masker import Masker                    # noqa: E402
 from dmm_net_b200.sharding import aggregate_throughput, shard_indices   # noqa: E402
 from dmm_net_b200.synth import default_cfg                      # noqa: E402
 from dmm_net_b200.utils.boxlist import BoxList                  # noqa: E402
@@ -71,6 +76,8 @@ def run(args):
     tplt = model.fill_template_dict(None, [BoxList(b) for b in tboxes], {"backbone_feature": f0, "refine_input_feat": f0},
                                     None, valid)
     mask_last = torch.stack([paste_masks(b, H, W, gen).squeeze(1) for b in tboxes], 0) * valid[:, :, None, None]
+    mask0 = mask_last                                                # reference masks of frame 0 (y_mask)
+    masker = Masker(threshold=0.5, padding=1)
     infos = {"args": None, "shape": (H, W), "extra_frame": [0] * B, "valid": valid}
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -80,25 +87,33 @@ def run(args):
             if t == 1:
                 t0.record()                                          # frame 0 is the warm-up
             fb = feats()
+            n_raw = args.proposals + 14                              # detections before NMS
+            raw = [BoxList(random_boxes(gen, n_raw, H, W, dev), (W, H)) for _ in range(B)]
+            m28 = [torch.sigmoid(3 * torch.randn(n_raw, 1, 28, 28, generator=gen, device=dev) + 1.5) for _ in range(B)]
+            pasted, tight = masker(m28, raw)                         # K8: all B x n_raw proposals in one launch
             props = []
             for b in range(B):
-                n = args.proposals - (b + t) % 3                     # ragged proposal counts, like NMS output
-                bl = BoxList(random_boxes(gen, n, H, W, dev))
-                bl.add_field("mask", paste_masks(bl.bbox, H, W, gen))
-                bl.add_field("scores", torch.rand(n, generator=gen, device=dev))
+                bl = BoxList(tight[b].float(), (W, H))               # mask post-processor: boxes become the tight boxes
+                bl.add_field("mask", pasted[b])
+                bl.add_field("scores", torch.rand(n_raw, generator=gen, device=dev))
                 props.append(bl)
+            props = filter_results(props, nms_thresh=0.8, max_proposals=args.proposals)      # K9: one launch per frame
+            prev = mask_last
             out, tplt, _, mask_last = model.inference(infos, props, fb, mask_last, tplt)
-            checks.append(float(out.sum()))
+            levels = ops.mask_pyramid(prev, mask0, out, 4)           # K6: decoder inputs of every object (identity decoder here)
+            labels = ops.merge_labels(out.view(B, F, -1), n_obj)     # K7: merged label map (evaluator.py:139-145)
+            checks.append(float(out.sum()) + float(levels[-1].sum()) + float(labels.sum()))
         t1.record()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) if args.frames > 1 else float("nan")
     frames = B * max(args.frames - 1, 0)
     rate = aggregate_throughput(frames, ms, dev) if args.frames > 1 else 0.0
     assert out.shape == (B, F, H, W) and all(c == c for c in checks)
+    assert labels.shape == (B, H * W) and int(labels.max()) <= F and levels[0].shape == (F, B, 3, (H + 3) // 4, (W + 3) // 4)
     assert float((out * (1 - valid)[:, :, None, None]).abs().sum()) == 0.0, "rows of invalid templates must stay zero"
     if rank == 0:
         print(f"clips={args.clips} ranks={world} frames/clip={args.frames} P~{args.proposals} F={F} {H}x{W}: "
-              f"{rate:.0f} (clip,frame) matches/s incl. synthetic proposal generation; last checksum {checks[-1]:.3f}")
+              f"{rate:.0f} (clip,frame) matches/s incl. paste + NMS + pyramid + labels; last checksum {checks[-1]:.3f}")
     if world > 1:
         dist.destroy_process_group()
     return rate

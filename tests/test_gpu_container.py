@@ -150,3 +150,17 @@ def test_synthetic_clip_loop_runs_sequential_frames():
     spec.loader.exec_module(mod)
     rate = mod.run(argparse.Namespace(clips=3, frames=4, proposals=9, objects=3, size=[64, 96]))
     assert rate > 0
+
+
+def test_synthetic_train_step_runs_and_produces_gradients():
+    """examples/synthetic_train_step.py (BASELINE configs[4] shape, shrunk): encoder -> K8 paste -> K5 -> training-mode
+    container (K2/K1/K3/K4 with backward) -> K6 pyramid (backward) -> decoder -> loss -> backward -> Adam."""
+    import argparse
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "synthetic_train_step.py")
+    spec = importlib.util.spec_from_file_location("synthetic_train_step", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    hist = mod.run(argparse.Namespace(steps=3, clips=2, frames=3, objects=2, proposals=7, arch="resnet18", size=[64, 96]))
+    assert len(hist) == 3 and all(h[0] == h[0] for h in hist)
