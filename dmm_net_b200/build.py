@@ -41,8 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o").replace(".cpp", ".o"))
         objs.append(obj)
-        if src.endswith(".cpp"):   # host-only code (mask packing): host compiler flags, OpenMP
-            cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3", "-c", os.path.join(CSRC, src), "-o", obj]
+        if src.endswith(".cpp"):   # host-only code (mask packing): host compiler flags, std::thread
+            cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread,-O3", "-c", os.path.join(CSRC, src), "-o", obj]
         else:
             extra = os.environ.get("DMM_BUILD_DEFINES", "").split()          # e.g. -DDMM_K2_TRACE (debug builds only)
             cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)

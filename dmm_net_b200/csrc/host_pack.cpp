@@ -7,11 +7,12 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #if defined(__x86_64__)
 #include <immintrin.h>
-#endif
-#ifdef _OPENMP
-#include <omp.h>
 #endif
 
 #include "../../include/dmm_b200.h"
@@ -40,6 +41,20 @@ __attribute__((target("avx2"))) void pack_row_avx2(const float* src, long long H
 }
 #endif
 
+#if defined(__x86_64__)
+__attribute__((target("avx512f"))) void pack_row_avx512(const float* src, long long HW, uint32_t* dst, long long words) {
+  const __m512 half = _mm512_set1_ps(0.5f);
+  const long long full = HW / 32;
+  for (long long j = 0; j < full; ++j) {
+    const float* x = src + 32 * j;
+    const uint32_t b0 = (uint32_t)_mm512_cmp_ps_mask(_mm512_loadu_ps(x), half, _CMP_GT_OQ);
+    const uint32_t b1 = (uint32_t)_mm512_cmp_ps_mask(_mm512_loadu_ps(x + 16), half, _CMP_GT_OQ);
+    dst[j] = b0 | (b1 << 16);
+  }
+  if (full < words) dst[full] = pack32_scalar(src + 32 * full, HW - 32 * full);
+}
+#endif
+
 void pack_row_scalar(const float* src, long long HW, uint32_t* dst, long long words) {
   const long long full = HW / 32;
   for (long long j = 0; j < full; ++j) dst[j] = pack32_scalar(src + 32 * j, 32);
@@ -57,29 +72,46 @@ extern "C" int dmm_host_pack_masks(const float* src, long long rows, long long H
   const long long words = (HW + 31) / 32;
 #if defined(__x86_64__)
   const bool avx2 = __builtin_cpu_supports("avx2");
+  const bool avx512 = __builtin_cpu_supports("avx512f");
 #else
-  const bool avx2 = false;
+  const bool avx2 = false, avx512 = false;
 #endif
   // split every row into pieces so that a handful of huge rows still spreads over all threads
   const long long piece_words = 1024;  // 128 KB of fp32 per task
   const long long pieces = (words + piece_words - 1) / piece_words;
   const long long tasks = rows * pieces;
-#ifdef _OPENMP
-  const int nt = threads > 0 ? threads : omp_get_max_threads();
-#pragma omp parallel for schedule(static) num_threads(nt)
-#endif
-  for (long long t = 0; t < tasks; ++t) {
-    const long long r = t / pieces, pc = t - r * pieces;
-    const long long w0 = pc * piece_words;
-    const long long w1 = w0 + piece_words < words ? w0 + piece_words : words;
-    const float* s = src + r * HW + 32 * w0;
-    const long long n = (32 * w1 < HW ? 32 * w1 : HW) - 32 * w0;
-    uint32_t* d = dst + r * words + w0;
+  // Plain std::threads per call, work claimed in blocks from an atomic counter.  (Round 1 used an OpenMP team: its idle
+  // workers SPIN after the parallel region, which under a cgroup CPU quota -- the GPU boxes give 128 logical CPUs a
+  // 16-CPU quota -- burns the quota and gets the whole process, kernel-launching thread included, throttled.)
+  long long nt = threads > 0 ? threads : (long long)std::thread::hardware_concurrency();
+  const long long block = 8;           // tasks per claim: 1 MB of fp32
+  if (nt > (tasks + block - 1) / block) nt = (tasks + block - 1) / block;
+  if (nt < 1) nt = 1;
+  std::atomic<long long> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const long long t0 = next.fetch_add(block, std::memory_order_relaxed);
+      if (t0 >= tasks) break;
+      const long long t1 = t0 + block < tasks ? t0 + block : tasks;
+      for (long long t = t0; t < t1; ++t) {
+        const long long r = t / pieces, pc = t - r * pieces;
+        const long long w0 = pc * piece_words;
+        const long long w1 = w0 + piece_words < words ? w0 + piece_words : words;
+        const float* s = src + r * HW + 32 * w0;
+        const long long n = (32 * w1 < HW ? 32 * w1 : HW) - 32 * w0;
+        uint32_t* d = dst + r * words + w0;
 #if defined(__x86_64__)
-    if (avx2) { pack_row_avx2(s, n, d, w1 - w0); continue; }
+        if (avx512) { pack_row_avx512(s, n, d, w1 - w0); continue; }
+        if (avx2) { pack_row_avx2(s, n, d, w1 - w0); continue; }
 #endif
-    pack_row_scalar(s, n, d, w1 - w0);
-  }
-  (void)threads;
+        pack_row_scalar(s, n, d, w1 - w0);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  pool.reserve((size_t)nt);
+  for (long long i = 1; i < nt; ++i) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
   return DMM_OK;
 }

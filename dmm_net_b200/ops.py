@@ -170,7 +170,7 @@ def packed_words(HW: int) -> int:
 
 def pack_masks_host(masks: torch.Tensor, mask_dims: int = 2, threads: int = 0, out: Optional[torch.Tensor] = None):
     """HOST fp32 masks [..., H, W] (mask_dims=2) or [..., HW] (mask_dims=1) -> HOST int32 bit planes [..., words]
-    (bit i of word j = pixel 32j+i > 0.5), packed by all host cores (OpenMP + AVX2 inside libdmm_b200).  Pass a pinned
+    (bit i of word j = pixel 32j+i > 0.5), packed by the host cores (std::thread + AVX-512/AVX2 inside libdmm_b200).  Pass a pinned
     ``out`` to make the following H2D copy asynchronous."""
     lib = _lib.load()
     assert not masks.is_cuda and masks.dtype == torch.float32
@@ -884,7 +884,7 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     """cost-build + solve for a batch whose inputs live in HOST memory (CPU fp32 tensors, pinned or not).
 
     Two routes feed the device at the same time:
-    * **packed**: the IoU needs only the thresholded bits, so the host cores pack the masks (OpenMP + AVX2, memory speed)
+    * **packed**: the IoU needs only the thresholded bits, so the host cores pack the masks (std::thread + AVX-512/AVX2, memory speed)
       and only bits cross PCIe: 0.86 MB instead of 27.5 MB of masks per match at the headline size (K1 on packed rows);
     * **raw**: while the cores are packing, the copy engine -- otherwise idle -- DMAs the fp32 masks of the first
       ``raw_fraction`` of the problems straight from pinned memory (K1 on fp32 rows, the TMA kernel).

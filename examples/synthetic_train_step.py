@@ -103,7 +103,8 @@ def run(args):
     params = list(enc.parameters()) + list(dec.parameters())
     if ddp:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        enc, dec = DDP(enc, device_ids=[local]), DDP(dec, device_ids=[local])
+        # several forwards per backward (one per frame / object): BN buffers must not be re-broadcast in between
+        enc, dec = DDP(enc, device_ids=[local], broadcast_buffers=False), DDP(dec, device_ids=[local], broadcast_buffers=False)
     opt = torch.optim.Adam(params, lr=1e-4)
     dmm = DMM_Model(default_cfg(10, 5), is_test=0).to(dev)           # train.yaml: 10 x 5 iterations
     masker = Masker(threshold=0.5, padding=1)

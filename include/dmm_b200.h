@@ -75,7 +75,7 @@ int dmm_mask_iou_pairwise_ptrs(const float* const* prop_ptrs, int ptrs_aligned16
  * bit i of word j of a row = (pixel 32*j + i) > 0.5f, zero past the row end; a row is dmm_packed_words(HW) uint32.
  * The IoU needs only these bits, so a producer that packs once moves 32x fewer bytes through K1:
  *   dmm_mask_pack_bits      device fp32 [rows][HW] -> device bits [rows][words]
- *   dmm_host_pack_masks     HOST fp32 -> HOST bits, multi-threaded (threads <= 0: all cores), so that masks held in
+ *   dmm_host_pack_masks     HOST fp32 -> HOST bits, multi-threaded with plain std::threads (threads <= 0: all cores), so that masks held in
  *                           host memory cross PCIe as 0.86 MB instead of 27.5 MB per match
  *   dmm_mask_iou_pairwise_packed   K1 on packed rows: same outputs, bit-identical to dmm_mask_iou_pairwise. */
 long long dmm_packed_words(long long HW);

@@ -11,8 +11,8 @@ pr = make_problems(B, P, O, H, W, D, seed=1, device="cuda")
 host = {k: getattr(pr, k).cpu().pin_memory() for k in ("prop_feat", "prop_mask", "tmpl_feat", "tmpl_mask", "prop_score")}
 layer = MatchModel(default_cfg(20, 5, 0.1, 0.3), is_test=1)
 res = torch.empty(B, O, 50, pin_memory=True)
-for th in (8, 16, 32):
-    for f in (0.0, 0.2, 0.3, 0.4, 0.5, None):
+for th in [int(x) for x in os.environ.get("E2E_THREADS", "8,16,32").split(",")]:
+    for f in [None if x == "auto" else float(x) for x in os.environ.get("E2E_FRACS", "0.0,0.2,0.3,0.4,0.5,auto").split(",")]:
         for i in range(5):
             if i == 2:
                 torch.cuda.synchronize(); t0 = time.perf_counter()
