@@ -28,6 +28,7 @@ SIGNATURES = {
                                         _vp, _vp, _sz, _vp]),
     "dmm_packed_words": (_ll, [_ll]),
     "dmm_host_pack_masks": (_i, [_vp, _ll, _ll, _vp, _i]),
+    "dmm_host_pack_masks2": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _i]),
     "dmm_mask_pack_bits": (_i, [_vp, _ll, _i, _vp, _vp]),
     "dmm_mask_iou_packed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "dmm_mask_iou_pairwise_packed": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f,

@@ -65,10 +65,11 @@ void pack_row_scalar(const float* src, long long HW, uint32_t* dst, long long wo
 
 extern "C" long long dmm_packed_words(long long HW) { return (HW + 31) / 32; }
 
-extern "C" int dmm_host_pack_masks(const float* src, long long rows, long long HW, uint32_t* dst, int threads) {
-  if (rows < 0 || HW < 0) return DMM_ERR_INVALID_ARGUMENT;
-  if (rows == 0 || HW == 0) return DMM_OK;
-  if (!src || !dst) return DMM_ERR_INVALID_ARGUMENT;
+namespace {
+
+struct PackJob { const float* src; long long rows; uint32_t* dst; };
+
+int pack_jobs(const PackJob* jobs, int njobs, long long HW, int threads) {
   const long long words = (HW + 31) / 32;
 #if defined(__x86_64__)
   const bool avx2 = __builtin_cpu_supports("avx2");
@@ -79,7 +80,10 @@ extern "C" int dmm_host_pack_masks(const float* src, long long rows, long long H
   // split every row into pieces so that a handful of huge rows still spreads over all threads
   const long long piece_words = 1024;  // 128 KB of fp32 per task
   const long long pieces = (words + piece_words - 1) / piece_words;
-  const long long tasks = rows * pieces;
+  long long first[3] = {0, 0, 0};      // task ranges of the (at most two) jobs
+  for (int j = 0; j < njobs; ++j) first[j + 1] = first[j] + jobs[j].rows * pieces;
+  const long long tasks = first[njobs];
+  if (tasks == 0) return DMM_OK;
   // Plain std::threads per call, work claimed in blocks from an atomic counter.  (Round 1 used an OpenMP team: its idle
   // workers SPIN after the parallel region, which under a cgroup CPU quota -- the GPU boxes give 128 logical CPUs a
   // 16-CPU quota -- burns the quota and gets the whole process, kernel-launching thread included, throttled.)
@@ -93,13 +97,15 @@ extern "C" int dmm_host_pack_masks(const float* src, long long rows, long long H
       const long long t0 = next.fetch_add(block, std::memory_order_relaxed);
       if (t0 >= tasks) break;
       const long long t1 = t0 + block < tasks ? t0 + block : tasks;
-      for (long long t = t0; t < t1; ++t) {
+      for (long long tt = t0; tt < t1; ++tt) {
+        const int j = (njobs > 1 && tt >= first[1]) ? 1 : 0;
+        const long long t = tt - first[j];
         const long long r = t / pieces, pc = t - r * pieces;
         const long long w0 = pc * piece_words;
         const long long w1 = w0 + piece_words < words ? w0 + piece_words : words;
-        const float* s = src + r * HW + 32 * w0;
+        const float* s = jobs[j].src + r * HW + 32 * w0;
         const long long n = (32 * w1 < HW ? 32 * w1 : HW) - 32 * w0;
-        uint32_t* d = dst + r * words + w0;
+        uint32_t* d = jobs[j].dst + r * words + w0;
 #if defined(__x86_64__)
         if (avx512) { pack_row_avx512(s, n, d, w1 - w0); continue; }
         if (avx2) { pack_row_avx2(s, n, d, w1 - w0); continue; }
@@ -114,4 +120,23 @@ extern "C" int dmm_host_pack_masks(const float* src, long long rows, long long H
   work();
   for (auto& th : pool) th.join();
   return DMM_OK;
+}
+
+}  // namespace
+
+extern "C" int dmm_host_pack_masks(const float* src, long long rows, long long HW, uint32_t* dst, int threads) {
+  if (rows < 0 || HW < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (rows == 0 || HW == 0) return DMM_OK;
+  if (!src || !dst) return DMM_ERR_INVALID_ARGUMENT;
+  const PackJob job = {src, rows, dst};
+  return pack_jobs(&job, 1, HW, threads);
+}
+
+extern "C" int dmm_host_pack_masks2(const float* src_a, long long rows_a, uint32_t* dst_a, const float* src_b,
+                                    long long rows_b, uint32_t* dst_b, long long HW, int threads) {
+  if (rows_a < 0 || rows_b < 0 || HW < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (HW == 0) return DMM_OK;
+  if ((rows_a > 0 && (!src_a || !dst_a)) || (rows_b > 0 && (!src_b || !dst_b))) return DMM_ERR_INVALID_ARGUMENT;
+  const PackJob jobs[2] = {{src_a, rows_a, dst_a}, {src_b, rows_b, dst_b}};
+  return pack_jobs(jobs, 2, HW, threads);
 }

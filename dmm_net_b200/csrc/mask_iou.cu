@@ -348,7 +348,9 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
       w.w = __ballot_sync(0xffffffffu, v.w > 0.5f);
       *reinterpret_cast<uint4*>(&bits[buf][u & 1][u >> 1][0]) = w;
     }
-    // this warp is done with the stage (its loads fed the ballots above): hand it back to the producer
+    // this warp is done with the stage (its loads fed the ballots above): hand it back to the producer.  The
+    // __syncwarp orders every lane's reads of the stage and of stage_item/stage_last before lane 0's release.
+    __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
     consumer_barrier();
     // ---- phase B: 16 warps = 8 words x 2 halves of the template rows ---------------------------------------

@@ -875,7 +875,27 @@ def _pinned(key, shape, dtype):
     return t
 
 
-_HOST_SPLIT = {}          # (P, O, HW) -> running estimate of seconds per problem for the two routes (pack, dma)
+_HOST_SPLIT = {}          # (P, O, HW) -> best measured seconds per problem of the two routes (pack, dma)
+_HOST_PENDING = {}        # (P, O, HW) -> measurements of the previous call, not yet folded in
+_STAGE_TURN, _STAGE_EVENT = {}, {}   # double-buffered pinned staging: next slot, and the H2D-done event of each slot
+
+
+def _fold_route_measurement(key):
+    """Rates are properties of the machine: keep the best seen (robust against a slow first call), and only trust a
+    route's measurement when it carried enough problems for its fixed costs not to dominate."""
+    pend = _HOST_PENDING.pop(key, None)
+    if pend is None:
+        return
+    e0, ev_dma, t_host, nraw, npk, B = pend
+    if not ev_dma.query():
+        _HOST_PENDING[key] = pend
+        return
+    old = _HOST_SPLIT.get(key, (float("inf"), float("inf")))
+    t_pack = min(old[0], t_host / npk) if npk >= max(4, B // 8) else old[0]
+    t_dma = min(old[1], e0.elapsed_time(ev_dma) * 1e-3 / nraw) if nraw >= max(4, B // 8) else old[1]
+    if t_pack < float("inf") and t_dma < float("inf"):
+        _HOST_SPLIT[key] = (t_pack, t_dma)
+
 
 
 def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, max_iter: int, proj_iter: int, lr: float,
@@ -913,6 +933,7 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     tmpl_mask = tmpl_mask.reshape(B, O, HW)
     key = (P, O, HW)
     can_raw = prop_mask.is_pinned() and tmpl_mask.is_pinned() and prop_mask.is_contiguous() and tmpl_mask.is_contiguous()
+    _fold_route_measurement(key)
     if raw_fraction is None:
         est = _HOST_SPLIT.get(key)
         # first call: nominal 100 GB/s of packing against 50 GB/s of PCIe; afterwards the best rates measured so far
@@ -925,9 +946,8 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     pm_raw = tm_raw = None
     ev_dma = None
     if nraw > 0:
-        copy_stream = _side_streams(dev)[0]
-        copy_stream.wait_stream(main)
-        with torch.cuda.stream(copy_stream):
+        copy_stream = _side_streams(dev)[0]                    # not ordered after `main`: the DMA may start while the previous
+        with torch.cuda.stream(copy_stream):                   # call's kernels still run (fresh buffers, read-only source)
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
             pm_raw, tm_raw = to_dev(prop_mask[:nraw]), to_dev(tmpl_mask[:nraw])
@@ -936,13 +956,25 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     npk = B - nraw
     t_host = 0.0
     if npk > 0:
-        _pinned("pb", (B, P, words), torch.int32), _pinned("tb", (B, O, words), torch.int32)   # allocated outside the timing
+        # Pinned staging buffers, sized for the whole batch (the split moves from call to call; re-pinning would cost more)
+        # and double-buffered: callers may issue the next call before this call's H2D has drained, and the packer must
+        # not overwrite bits that are still being copied.  The event of a slot is waited for before the slot is reused.
+        slot = _STAGE_TURN.get(key, 0)
+        _STAGE_TURN[key] = slot ^ 1
+        pb_full, tb_full = _pinned(("pb", slot), (B, P, words), torch.int32), _pinned(("tb", slot), (B, O, words), torch.int32)
+        busy = _STAGE_EVENT.get((key, slot))
+        if busy is not None:
+            busy.synchronize()
         t0 = time.perf_counter()
-        # staging buffers are sized for the whole batch (the split moves from call to call; re-pinning would cost more)
-        pb = pack_masks_host(prop_mask[nraw:], mask_dims=1, threads=th, out=_pinned("pb", (B, P, words), torch.int32)[:npk])
-        tb = pack_masks_host(tmpl_mask[nraw:], mask_dims=1, threads=th, out=_pinned("tb", (B, O, words), torch.int32)[:npk])
+        pb, tb = pb_full[:npk], tb_full[:npk]
+        rc = lib.dmm_host_pack_masks2(_VP(prop_mask[nraw:].data_ptr()), npk * P, _VP(pb.data_ptr()),
+                                      _VP(tmpl_mask[nraw:].data_ptr()), npk * O, _VP(tb.data_ptr()), HW, th)   # one thread team
+        _lib.check(rc, "dmm_host_pack_masks2")
         t_host = time.perf_counter() - t0
         pbd, tbd = to_dev(pb), to_dev(tb)
+        done = torch.cuda.Event()
+        done.record(main)
+        _STAGE_EVENT[(key, slot)] = done
     pf, tf, sc = to_dev(prop_feat.contiguous()), to_dev(tmpl_feat.contiguous()), to_dev(prop_score.contiguous())
     n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
     sl = lambda t, a, b: None if t is None else t[a:b]
@@ -967,16 +999,9 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
         R, Bm, ms, ds, Xf, logic, n_list = relax_solve(sim, sc, n_prop, n_tmpl, max_iter, proj_iter, lr, True, True,
                                                        bool(is_test))
     if nraw > 0 and npk > 0:
-        # update the route estimates for the next call; the DMA has finished by the time K1 ran, but do not block here:
-        # query, and keep the old estimate if the event is not ready yet
-        # (rates are properties of the machine: keep the best seen, which is robust against a slow first call, and only
-        # trust a route's measurement when it carried enough problems for its fixed costs not to dominate)
-        if ev_dma.query():
-            old = _HOST_SPLIT.get(key, (float("inf"), float("inf")))
-            t_pack = min(old[0], t_host / npk) if npk >= max(4, B // 8) else old[0]
-            t_dma = min(old[1], e0.elapsed_time(ev_dma) * 1e-3 / nraw) if nraw >= max(4, B // 8) else old[1]
-            if t_pack < float("inf") and t_dma < float("inf"):
-                _HOST_SPLIT[key] = (t_pack, t_dma)
+        # route measurements of this call; folded into the estimate at the start of the next call (the DMA may still be
+        # running here when it is the longer route -- never block on it)
+        _HOST_PENDING[key] = (e0, ev_dma, t_host, nraw, npk, B)
     h2d = 4 * (prop_feat.numel() + tmpl_feat.numel() + prop_score.numel()) + 4 * npk * (P + O) * words + \
         4 * nraw * (P + O) * HW
     return {"cos": cos, "iou": iou, "sim": sim, "R": R, "Bmat": Bm, "logic": logic, "X_final": Xf,

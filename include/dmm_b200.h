@@ -80,6 +80,9 @@ int dmm_mask_iou_pairwise_ptrs(const float* const* prop_ptrs, int ptrs_aligned16
  *   dmm_mask_iou_pairwise_packed   K1 on packed rows: same outputs, bit-identical to dmm_mask_iou_pairwise. */
 long long dmm_packed_words(long long HW);
 int dmm_host_pack_masks(const float* src_host, long long rows, long long HW, uint32_t* dst_host, int threads);
+/* two row sets of the same HW (a problem's proposal and template masks) packed by ONE thread team */
+int dmm_host_pack_masks2(const float* src_a, long long rows_a, uint32_t* dst_a, const float* src_b, long long rows_b,
+                         uint32_t* dst_b, long long HW, int threads);
 int dmm_mask_pack_bits(const float* masks, long long rows, int HW, uint32_t* bits, void* stream);
 size_t dmm_mask_iou_packed_workspace_bytes(int B, int P, int O, int words, int two_template_sets);
 int dmm_mask_iou_pairwise_packed(const uint32_t* prop_bits, long long prop_bstride_words, const uint32_t* tmpl_bits,
