@@ -293,7 +293,7 @@ def main():
         if world > 1:
             dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(3):                                            # pinned staging buffers exist now; the raw/packed split
+        for _ in range(6):                                            # pinned staging buffers exist now; the raw/packed split
             e2e_step()                                                #   settles on the measured route speeds
             torch.cuda.synchronize()
         t_wall = time.perf_counter()

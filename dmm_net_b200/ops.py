@@ -881,8 +881,9 @@ _STAGE_TURN, _STAGE_EVENT = {}, {}   # double-buffered pinned staging: next slot
 
 
 def _fold_route_measurement(key):
-    """Rates are properties of the machine: keep the best seen (robust against a slow first call), and only trust a
-    route's measurement when it carried enough problems for its fixed costs not to dominate."""
+    """Exponential average of the measured seconds per problem of each route (under several ranks per host the packing
+    rate depends on what the other ranks are doing, so the estimate has to follow it); a route's measurement only counts
+    when it carried enough problems for its fixed costs not to dominate."""
     pend = _HOST_PENDING.pop(key, None)
     if pend is None:
         return
@@ -890,11 +891,15 @@ def _fold_route_measurement(key):
     if not ev_dma.query():
         _HOST_PENDING[key] = pend
         return
-    old = _HOST_SPLIT.get(key, (float("inf"), float("inf")))
-    t_pack = min(old[0], t_host / npk) if npk >= max(4, B // 8) else old[0]
-    t_dma = min(old[1], e0.elapsed_time(ev_dma) * 1e-3 / nraw) if nraw >= max(4, B // 8) else old[1]
-    if t_pack < float("inf") and t_dma < float("inf"):
-        _HOST_SPLIT[key] = (t_pack, t_dma)
+    old = _HOST_SPLIT.get(key)
+    new_pack = t_host / npk if npk >= max(4, B // 8) else None
+    new_dma = e0.elapsed_time(ev_dma) * 1e-3 / nraw if nraw >= max(4, B // 8) else None
+    if old is None:
+        if new_pack is not None and new_dma is not None:
+            _HOST_SPLIT[key] = (new_pack, new_dma)
+        return
+    mix = lambda o, n: o if n is None else 0.5 * (o + n)
+    _HOST_SPLIT[key] = (mix(old[0], new_pack), mix(old[1], new_dma))
 
 
 
@@ -936,9 +941,9 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     _fold_route_measurement(key)
     if raw_fraction is None:
         est = _HOST_SPLIT.get(key)
-        # first call: nominal 100 GB/s of packing against 50 GB/s of PCIe; afterwards the best rates measured so far
+        # first call: nominal 100 GB/s of packing against 50 GB/s of PCIe; afterwards the measured rates
         t_pack, t_dma = est if est else (1.0, 2.0)
-        raw_fraction = min(0.6, t_pack / (t_pack + t_dma))
+        raw_fraction = min(0.9, t_pack / (t_pack + t_dma))
     nraw = int(round(B * float(raw_fraction))) if can_raw and B >= 4 else 0
     nraw = max(0, min(nraw, B))
     main = torch.cuda.current_stream(dev)
