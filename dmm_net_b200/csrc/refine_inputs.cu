@@ -181,17 +181,27 @@ __global__ void __launch_bounds__(256) merge_labels_kernel(const float* __restri
     int arg[step];
 #pragma unroll
     for (int j = 0; j < step; ++j) { best[j] = 0.f; arg[j] = 0; }
-    for (int o = 0; o < n; ++o) {
-      float v[step];
-      if constexpr (VEC) {
-        const float4 f = ld_stream_f4(m + (long long)o * HW + 4 * q);
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-      } else {
-        v[0] = ld_stream_f1(m + (long long)o * HW + q);
+    for (int o0 = 0; o0 < n; o0 += 4) {                     // four objects' loads in flight, compared in object order
+      float v[4][step];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int o = min(o0 + k, n - 1);                    // clamped (re-reads the last object; never compared)
+        if constexpr (VEC) {
+          const float4 f = ld_stream_f4(m + (long long)o * HW + 4 * q);
+          v[k][0] = f.x; v[k][1] = f.y; v[k][2] = f.z; v[k][3] = f.w;
+        } else {
+          v[k][0] = ld_stream_f1(m + (long long)o * HW + q);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < step; ++j)
-        if (o == 0 || v[j] > best[j]) { best[j] = v[j]; arg[j] = o + 1; }
+      for (int k = 0; k < 4; ++k) {
+        const int o = o0 + k;
+        if (o < n) {
+#pragma unroll
+          for (int j = 0; j < step; ++j)
+            if (o == 0 || v[k][j] > best[j]) { best[j] = v[k][j]; arg[j] = o + 1; }
+        }
+      }
     }
     unsigned char r[step];
 #pragma unroll
@@ -290,9 +300,8 @@ extern "C" int dmm_merge_labels(const float* masks, long long bstride, int B, in
   if (O > 254) return DMM_ERR_UNSUPPORTED_SHAPE;
   const bool vec = HW % 4 == 0 && aligned16(masks) && bstride % 4 == 0 && ((uintptr_t)label & 3u) == 0;
   const int nq = vec ? HW / 4 : HW;
-  long long per_b = (nq + 255) / 256;
-  const long long cap = (8LL * kNumSMs + B - 1) / B;      // ~8 CTAs per SM over the whole batch
-  if (per_b > cap) per_b = cap < 1 ? 1 : cap;
+  long long per_b = (nq + 1023) / 1024;                     // four items per thread: every thread does the same work
+  if (per_b < 1) per_b = 1;
   const long long blocks = per_b * B;
   if (blocks > 0x7fffffffLL) return DMM_ERR_UNSUPPORTED_SHAPE;
   if (vec) merge_labels_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(masks, bstride, B, O, HW, n_valid, label, (int)per_b);
