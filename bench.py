@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (rank 0, N=1)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--secondary-steps", type=int, default=5, help="timed steps of the full-layer secondary metric (0: skip)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads for mask packing (0: cgroup-aware default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -310,6 +311,25 @@ def main():
         e2e_ms = t.item()
     e2e_val = world * Be * args.e2e_steps / (e2e_ms * 1e-3)
     d2h = (res_host.numel() + res_ms.numel()) * 4
+
+    # ---- secondary: the full layer incl. assignment-apply (K4), resident inputs, this rank only ------
+    secondary = None
+    if rank == 0 and args.secondary_steps > 0:
+        with torch.no_grad():
+            full = lambda: layer.forward_many(pr.prop_feat, pr.prop_mask, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score)["full_outmask"]
+            for _ in range(2):
+                out_full = full()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(args.secondary_steps):
+                out_full = full()
+            b.record()
+            torch.cuda.synchronize()
+            ms_full = a.elapsed_time(b) / args.secondary_steps
+        secondary = {"full_layer_matches_per_s_per_gpu": B / (ms_full * 1e-3), "full_layer_ms_per_step": ms_full,
+                     "what": "MatchModel.forward_many incl. K4 assignment-apply writing full_outmask [B,O,H,W], resident inputs"}
+        del out_full
     h2d = e2e_info.get("h2d", 0)
 
     if rank == 0:
@@ -331,6 +351,7 @@ def main():
                     "api": "MatchModel.forward_many_host: pinned host fp32 inputs; the host cores bit-pack most masks (bits "
                            "cross PCIe) while the copy engine DMAs the rest as fp32; features+scores H2D, R and match_score D2H"},
             "gpu_launches": launches,
+            "secondary": secondary,
             "roofline": {"bound": "hbm", "kernel": "mask_iou_partial_kernel(+finalize)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": MASK_BYTES_PER_MATCH * B, "kernel_ms": k1_ms},
