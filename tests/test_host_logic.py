@@ -45,3 +45,51 @@ def test_shape_asserts_fire_before_any_kernel():
         layer(pr.prop_feat, pr.prop_mask[0], [pr.tmpl_feat], pr.tmpl_mask, pr.prop_score)
     with pytest.raises(AssertionError):                          # one score per proposal
         layer(pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, pr.prop_score[:3])
+
+
+def test_rows_around_the_layer_refuse_cpu_tensors_and_keep_the_reference_asserts():
+    """K6-K9 host wrappers: no CPU fallback (RuntimeError before any kernel), shape asserts like the reference's"""
+    from dmm_net_b200.utils.boxlist import BoxList
+    from dmm_net_b200.utils.boxlist_ops import filter_results
+    from dmm_net_b200.utils.masker import Masker
+    m = torch.rand(2, 3, 8, 8)
+    with pytest.raises(RuntimeError):
+        ops.mask_pyramid(m, m, m, 4)
+    with pytest.raises(RuntimeError):
+        ops.merge_labels(m.view(2, 3, 64))
+    with pytest.raises(RuntimeError):
+        ops.paste_masks(torch.rand(3, 1, 28, 28), torch.rand(3, 4), 16, 16)
+    with pytest.raises(RuntimeError):
+        ops.box_nms(torch.rand(5, 4), torch.rand(5), 0.5)
+    with pytest.raises(AssertionError):                          # init_pred_inst is [B,O,H,W] (trainer.py:184 CHECK4D)
+        ops.mask_pyramid(m, m, m.view(2, 3, 64), 4)
+    boxes = BoxList(torch.rand(3, 4), (16, 16))
+    with pytest.raises(AssertionError):                          # masker.py:219 "Number of objects should be the same."
+        Masker(0.5)([torch.rand(2, 1, 28, 28)], [boxes])
+    with pytest.raises(AssertionError):                          # masker.py:214 "Masks and boxes should have the same length."
+        Masker(0.5)([torch.rand(3, 1, 28, 28)] * 2, [boxes])
+    assert filter_results([]) == []
+    empty = BoxList(torch.zeros(0, 4), (16, 16))
+    empty.add_field("scores", torch.zeros(0))
+    assert len(filter_results([empty])[0]) == 0                  # nothing to suppress: no kernel, no sync
+
+
+def test_boxlist_indexing_carries_fields():
+    from dmm_net_b200.utils.boxlist import BoxList
+    b = BoxList(torch.arange(20.).view(5, 4), (10, 10))
+    b.add_field("scores", torch.arange(5.))
+    b.add_field("mask", torch.arange(5)[:, None, None, None].expand(5, 1, 2, 2))
+    k = b[torch.tensor([3, 0])]
+    assert len(k) == 2 and k.size == (10, 10) and k.get_field("scores").tolist() == [3.0, 0.0]
+    assert k.get_field("mask")[:, 0, 0, 0].tolist() == [3, 0] and k.bbox[0].tolist() == [12.0, 13.0, 14.0, 15.0]
+
+
+def test_cosine_impl_names_and_packed_word_count():
+    assert ops.COSINE_IMPLS == {"auto": 0, "simt": 1, "tc": 2}
+    lib = __import__("dmm_net_b200._lib", fromlist=["load"]).load()
+    assert lib.dmm_packed_words(256 * 448) == 3584
+    assert lib.dmm_paste_masks_workspace_bytes(50) >= 50 * 16
+    import ctypes
+    h, w = ctypes.c_int(), ctypes.c_int()
+    assert lib.dmm_mask_pyramid_level_size(255, 447, 3, ctypes.byref(h), ctypes.byref(w)) == 0 and (h.value, w.value) == (8, 14)
+    assert lib.dmm_mask_pyramid_level_size(255, 447, 5, ctypes.byref(h), ctypes.byref(w)) == 1      # more than 5 levels
