@@ -157,6 +157,123 @@ __global__ void paste_tight_finalize_kernel(const int* __restrict__ ws, long lon
   else { t[0] = w.x; t[1] = w.y; t[2] = -w.z; t[3] = -w.w; }
 }
 
+// ---- K10: fused paste + assignment apply ("lazy paste") ---------------------------------------------------------
+// out[b, row(o), :] = sum_p Bmat[b,o,p] * paste(mask[src[b,p]], box[src[b,p]])      (match_model.py:144 on top of masker.py)
+// The eval pipeline pastes P soft masks per frame (P*HW*4 bytes written), reads them all back for the IoU and once more
+// for the apply, although the IoU needs one bit per pixel (K8's bit rows -> packed K1) and the apply needs the <= O
+// SELECTED proposals.  This kernel pastes only those, scaled, straight into the output rows: per frame O*HW*4 bytes
+// written and nothing read but the 28x28 heads.  Same tap arithmetic as K8 and the same fmaf(v, m, acc) accumulation in
+// ascending proposal order as K4, so the result is bit-identical to K8 followed by K4.
+constexpr int kMaxSrc = 8;       // source masks resident in shared memory per pass
+
+struct PasteApplyParams {
+  const float* coef;             // [B][O][MS]
+  const float* masks;            // [Nsrc][M][M]
+  const float* boxes;            // [Nsrc][4]
+  const int* src;                // [B][P] row of masks/boxes for column p, or < 0
+  const int* n_prop; const int* n_tmpl; const int* row_map;
+  float* out; long long out_bs;
+  int B, P, O, MS, O_out, M, pad, im_h, im_w, rows_per_cta, zero_fill;
+  float scale;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) paste_apply_kernel(const PasteApplyParams p) {
+  extern __shared__ float sm_src[];               // [kMaxSrc][Mp*Mp]
+  __shared__ int s_col[128];                      // non-zero columns of this output row, ascending
+  __shared__ float s_val[128];
+  __shared__ int s_cnt, s_o;
+  __shared__ BoxI s_bx[kMaxSrc];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.y / p.O_out, f = blockIdx.y % p.O_out;
+  const int Mp = p.M + 2 * p.pad;
+  const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
+  const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
+  if (tid == 0) {                                  // which template row lands in output row f (row_map may scatter)
+    int o = -1;
+    if (!p.row_map) o = f < nt ? f : -1;
+    else for (int k = 0; k < nt; ++k) if (p.row_map[(long long)b * p.O + k] == f) o = k;
+    s_o = o;
+    s_cnt = 0;
+  }
+  __syncthreads();
+  const int o = s_o;
+  if (o < 0 && !p.zero_fill) return;
+  if (o >= 0 && tid < 32) {                        // warp 0: ballot-compact the non-zero coefficients of row o
+    const float* crow = p.coef + ((long long)b * p.O + o) * p.MS;
+    int cnt = 0;
+    for (int c0 = 0; c0 < np; c0 += 32) {
+      const int c = c0 + lane;
+      const float v = c < np ? crow[c] : 0.f;
+      const bool nz = v != 0.f && p.src[(long long)b * p.P + min(c, p.P - 1)] >= 0 && c < np;
+      const unsigned mk = __ballot_sync(0xffffffffu, nz);
+      if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s_col[pos] = c; s_val[pos] = v; }
+      cnt += __popc(mk);
+    }
+    if (lane == 0) s_cnt = cnt;
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  const int row_lo = blockIdx.x * p.rows_per_cta, row_hi = min(row_lo + p.rows_per_cta, p.im_h);
+  constexpr int step = VEC ? 4 : 1;
+  const int groups = (p.im_w + step - 1) / step;
+  const int items = (row_hi - row_lo) * groups;
+  float* orow = p.out + (long long)b * p.out_bs + (long long)f * p.im_h * p.im_w;
+  for (int e0 = 0; e0 == 0 || e0 < cnt; e0 += kMaxSrc) {     // one pass per kMaxSrc sources (a single pass in eval mode)
+    const int ne = min(kMaxSrc, cnt - e0);
+    __syncthreads();
+    for (int k = 0; k < ne; ++k) {
+      const int srow = p.src[(long long)b * p.P + s_col[e0 + k]];
+      const float* src = p.masks + (long long)srow * p.M * p.M;
+      for (int i = tid; i < Mp * Mp; i += kThreads) {
+        const int y = i / Mp - p.pad, x = i % Mp - p.pad;
+        sm_src[k * Mp * Mp + i] = (y >= 0 && y < p.M && x >= 0 && x < p.M) ? src[y * p.M + x] : 0.f;
+      }
+      if (tid == 0) s_bx[k] = expand_box(p.boxes + 4LL * srow, p.scale);
+    }
+    __syncthreads();
+    for (int it = tid; it < items; it += kThreads) {
+      const int Y = row_lo + it / groups, X = (it % groups) * step;
+      float acc[step];
+      if (e0 == 0) {
+#pragma unroll
+        for (int k = 0; k < step; ++k) acc[k] = 0.f;
+      } else {                                      // later passes accumulate on top of what the earlier ones wrote
+        if constexpr (VEC) {
+          const float4 q = *reinterpret_cast<const float4*>(orow + (long long)Y * p.im_w + X);
+          acc[0] = q.x; acc[1] = q.y; acc[2] = q.z; acc[3] = q.w;
+        } else {
+          acc[0] = orow[(long long)Y * p.im_w + X];
+        }
+      }
+      for (int k = 0; k < ne; ++k) {
+        const BoxI bx = s_bx[k];
+        const int x0c = max(bx.x0, 0), x1c = min(bx.x1 + 1, p.im_w);
+        const int y0c = max(bx.y0, 0), y1c = min(bx.y1 + 1, p.im_h);
+        if (Y < y0c || Y >= y1c || X + step <= x0c || X >= x1c) continue;
+        const float v = s_val[e0 + k];
+        const float sc_y = (float)Mp / (float)bx.h, sc_x = (float)Mp / (float)bx.w;
+        const Tap ty = tap(Y - bx.y0, sc_y, Mp);
+        const float* r0 = sm_src + k * Mp * Mp + ty.i0 * Mp;
+        const float* r1 = sm_src + k * Mp * Mp + ty.i1 * Mp;
+#pragma unroll
+        for (int j = 0; j < step; ++j) {
+          const int Xj = X + j;
+          if (Xj >= x0c && Xj < x1c) {
+            const Tap tx = tap(Xj - bx.x0, sc_x, Mp);
+            const float top = fmaf(tx.l0, r0[tx.i0], __fmul_rn(tx.l1, r0[tx.i1]));
+            const float bot = fmaf(tx.l0, r1[tx.i0], __fmul_rn(tx.l1, r1[tx.i1]));
+            const float m = fmaf(ty.l0, top, __fmul_rn(ty.l1, bot));
+            acc[j] = cnt == 1 ? __fmul_rn(v, m) : fmaf(v, m, acc[j]);      // K4: scaled copy for one source, fmaf chain else
+          }
+        }
+      }
+      if constexpr (VEC) st_stream_f4(orow + (long long)Y * p.im_w + X, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      else orow[(long long)Y * p.im_w + X] = acc[0];
+    }
+  }
+}
+
 // ---- K9 ------------------------------------------------------------------------------------------------------
 constexpr int kNmsMax = 1024;
 
@@ -273,6 +390,42 @@ extern "C" int dmm_paste_masks(const float* masks, const float* boxes, int N, in
     rc = check_launch();
   }
   return rc;
+}
+
+extern "C" int dmm_paste_apply(const float* Bmat, const float* masks, const float* boxes, const int* src_index, int B, int P,
+                               int O, int MS, int M, int padding, int im_h, int im_w, const int* n_prop, const int* n_tmpl,
+                               const int* row_map, int O_out, int zero_fill, float* out, long long out_bstride,
+                               void* stream) {
+  if (B < 0 || P < 0 || O < 0 || MS < P || M <= 0 || padding < 1 || im_h < 0 || im_w < 0 || O_out < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (M + 2 * padding > kMaxMp || P > 128 || (long long)B * O_out > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
+  if (B == 0 || O_out == 0 || im_h == 0 || im_w == 0) return DMM_OK;
+  if (!out || (O > 0 && P > 0 && (!Bmat || !masks || !boxes || !src_index))) return DMM_ERR_INVALID_ARGUMENT;
+  PasteApplyParams kp;
+  kp.coef = Bmat; kp.masks = masks; kp.boxes = boxes; kp.src = src_index; kp.n_prop = n_prop; kp.n_tmpl = n_tmpl;
+  kp.row_map = row_map; kp.out = out; kp.out_bs = out_bstride;
+  kp.B = B; kp.P = P; kp.O = O; kp.MS = MS; kp.O_out = O_out; kp.M = M; kp.pad = padding; kp.im_h = im_h; kp.im_w = im_w;
+  kp.zero_fill = zero_fill;
+  kp.scale = (float)((double)(M + 2 * padding) / (double)M);
+  const long long rows_total = (long long)B * O_out;
+  long long slabs = (16LL * kNumSMs + rows_total - 1) / rows_total;
+  const long long max_slabs = (im_h + 3) / 4;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  kp.rows_per_cta = (int)((im_h + slabs - 1) / slabs);
+  slabs = (im_h + kp.rows_per_cta - 1) / kp.rows_per_cta;
+  const int Mp = M + 2 * padding;
+  const size_t smem = (size_t)kMaxSrc * Mp * Mp * sizeof(float);
+  const bool vec = im_w % 4 == 0 && aligned16(out) && out_bstride % 4 == 0;
+  dim3 grid((unsigned)slabs, (unsigned)rows_total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) {
+    DMM_CUDA_TRY(cudaFuncSetAttribute(paste_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    paste_apply_kernel<true><<<grid, kThreads, smem, st>>>(kp);
+  } else {
+    DMM_CUDA_TRY(cudaFuncSetAttribute(paste_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    paste_apply_kernel<false><<<grid, kThreads, smem, st>>>(kp);
+  }
+  return check_launch();
 }
 
 extern "C" int dmm_box_nms(const float* boxes, const float* scores, const int* n_boxes, int F, int n_max, float thresh,

@@ -647,6 +647,40 @@ def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, im_h: int, im_w: int, 
     return out
 
 
+def paste_apply(Bm: torch.Tensor, masks: torch.Tensor, boxes: torch.Tensor, src_index: torch.Tensor, im_h: int, im_w: int,
+                n_prop=None, n_tmpl=None, row_map: Optional[torch.Tensor] = None, O_out: Optional[int] = None,
+                zero_fill: bool = True, padding: int = 1) -> torch.Tensor:
+    """Fused paste + assignment apply ("lazy paste", K10): out[b, row(o)] = sum_p Bm[b,o,p] * paste(masks[src_index[b,p]]).
+
+    Bm [B,O,MS]; masks [Nsrc,1,M,M] / [Nsrc,M,M] mask-head outputs and boxes [Nsrc,4] of ALL detections; src_index [B,P]
+    int32 = which detection sits behind column p of problem b (-1: none) -- the NMS keep list.  Returns [B,O_out,im_h,im_w],
+    bit-identical to ``assign_apply(Bm, paste_masks(...)["pasted"] gathered by src_index)`` without ever writing or reading
+    the P pasted masks.  Inference only."""
+    lib = _lib.load()
+    Bm = _cuda_f32(Bm, "Bmat")
+    masks, boxes = _cuda_f32(masks, "masks"), _cuda_f32(boxes, "boxes")
+    B, O, MS = Bm.shape
+    M = masks.shape[-1]
+    dev = Bm.device
+    src_index = torch.as_tensor(src_index, device=dev).to(torch.int32).contiguous()
+    P = src_index.shape[1]
+    assert src_index.shape == (B, P) and MS >= P and boxes.shape == (masks.shape[0], 4), (src_index.shape, Bm.shape, boxes.shape)
+    if row_map is not None:
+        row_map = torch.as_tensor(row_map, device=dev).to(torch.int32).contiguous()
+        assert row_map.shape == (B, O)
+    O_out = int(O if O_out is None else O_out)
+    out = torch.empty(B, O_out, im_h, im_w, device=dev)
+    step = max(1, 65535 // max(O_out, 1))
+    for s in range(0, B, step):
+        e = min(B, s + step)
+        sl = lambda t: None if t is None else t[s:e]
+        rc = lib.dmm_paste_apply(_p(Bm[s:e]), _p(masks), _p(boxes), _p(src_index[s:e]), e - s, P, O, MS, M, int(padding),
+                                 int(im_h), int(im_w), _p(sl(_counts(n_prop, B, dev))), _p(sl(_counts(n_tmpl, B, dev))),
+                                 _p(sl(row_map)), O_out, int(zero_fill), _p(out[s:e]), O_out * im_h * im_w, _stream())
+        _lib.check(rc, "dmm_paste_apply")
+    return out
+
+
 def box_nms(boxes: torch.Tensor, scores: torch.Tensor, thresh: float, max_keep: int = 0, n_boxes=None):
     """boxes [F,n,4] (or [n,4]), scores [F,n] (or [n]) -> (keep [F,n] int64 kept indices in score order, -1 padded; n_keep
     [F] int32).  Greedy NMS with the legacy +1 widths, one CTA per frame (boxlist_ops.py:15-29)."""

@@ -229,6 +229,19 @@ int dmm_paste_masks(const float* masks, const float* boxes, int N, int M, int pa
                     float* pasted, uint32_t* bits, long long* tight, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ---- K10: fused paste + assignment apply ("lazy paste") -----------------------------------------------------------
+ * out[b, row(o), :] = sum_p Bmat[b,o,p] * paste(masks[src_index[b,p]], boxes[src_index[b,p]])
+ * = dmm_assign_apply on top of dmm_paste_masks without ever materialising the P pasted proposal masks: with K8's bit rows
+ * feeding the packed K1 entry, the eval pipeline writes O*HW*4 bytes per frame instead of writing P*HW*4, reading them for
+ * the IoU and reading the selected ones again for the apply.  Bit-identical to dmm_paste_masks followed by dmm_assign_apply.
+ * Bmat [B][O][MS]; masks [Nsrc][M][M], boxes [Nsrc][4]; src_index [B][P] = row of masks/boxes behind column p of problem
+ * b (< 0: none; this is where the NMS keep list plugs in); n_prop / n_tmpl / row_map / O_out / zero_fill as in
+ * dmm_assign_apply; out [B][O_out][im_h][im_w].  Inference only (no backward).  P <= 128, B*O_out <= 65535.
+ */
+int dmm_paste_apply(const float* Bmat, const float* masks, const float* boxes, const int* src_index, int B, int P, int O,
+                    int MS, int M, int padding, int im_h, int im_w, const int* n_prop, const int* n_tmpl,
+                    const int* row_map, int O_out, int zero_fill, float* out, long long out_bstride, void* stream);
+
 /* ---- K9: box NMS ---------------------------------------------------------------------------------------------
  * Replaces filter_results (dmm/utils/boxlist_ops.py:15-29) -> maskrcnn_benchmark.layers.nms (un-vendored): greedy,
  * score-descending (ties: lower index first), IoU with the legacy +1 pixel widths, suppress when IoU > thresh, then

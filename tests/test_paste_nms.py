@@ -184,3 +184,40 @@ def test_filter_results_mirror():
         want = rorc.filter_results(b, s, 0.6, 20)
         assert torch.equal(bl.get_field("mask").cpu(), want)
         assert torch.equal(bl.bbox.cpu(), b[want])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["eval_one_hot", "train_many", "more_than_8_sources"])
+def test_k10_lazy_paste_apply_is_bit_identical_to_paste_then_apply(mode):
+    """K10 pastes only the selected detections, scaled, straight into the output rows == K8 (all P) then K4"""
+    from dmm_net_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    B, P, O, F_, H, W, Nsrc = 3, 20, 4, 5, 72, 100, 90
+    masks = torch.sigmoid(3 * torch.randn(Nsrc, 1, 28, 28, generator=gen)).cuda()
+    xy = torch.rand(Nsrc, 2, generator=gen) * torch.tensor([W * 0.6, H * 0.6])
+    boxes = torch.cat([xy, xy + torch.rand(Nsrc, 2, generator=gen) * torch.tensor([W * 0.5, H * 0.5]) + 2], 1)
+    boxes[:, 0::2].clamp_(0, W - 1)
+    boxes[:, 1::2].clamp_(0, H - 1)
+    boxes = boxes.cuda()
+    src = torch.stack([torch.randperm(Nsrc, generator=gen)[:P] for _ in range(B)]).to(torch.int32)   # the "NMS keep list"
+    n_prop = torch.tensor([20, 13, 20], dtype=torch.int32)
+    n_tmpl = torch.tensor([4, 2, 3], dtype=torch.int32)
+    src[1, 13:] = -1
+    Bm = torch.zeros(B, O, 21)
+    if mode == "eval_one_hot":
+        for b in range(B):
+            for o in range(O):
+                Bm[b, o, int(torch.randint(0, int(n_prop[b]), (), generator=gen))] = float(torch.rand((), generator=gen)) + 0.1
+    else:
+        dens = 0.25 if mode == "train_many" else 0.7
+        Bm[:, :, :P] = torch.rand(B, O, P, generator=gen) * (torch.rand(B, O, P, generator=gen) < dens)
+    row_map = torch.tensor([[0, 2, 3, 4], [1, 4, -1, -1], [4, 0, 2, -1]], dtype=torch.int32)
+    pasted = ops.paste_masks(masks, boxes, H, W)["pasted"]                                 # every detection
+    gathered = pasted[src.clamp(min=0).long().cuda()]                                       # [B,P,H,W]
+    want = ops.assign_apply(Bm.cuda(), gathered.view(B, P, -1), None, n_prop.cuda(), n_tmpl.cuda(), row_map.cuda(), F_)
+    got = ops.paste_apply(Bm.cuda(), masks, boxes, src.cuda(), H, W, n_prop.cuda(), n_tmpl.cuda(), row_map.cuda(), F_)
+    assert torch.equal(got.view(B, F_, -1), want)
+    assert got.abs().sum() > 0
+    plain = ops.paste_apply(Bm.cuda(), masks, boxes, src.cuda(), H, W, n_prop.cuda(), n_tmpl.cuda())     # no scatter
+    want_plain = ops.assign_apply(Bm.cuda(), gathered.view(B, P, -1), None, n_prop.cuda(), n_tmpl.cuda())
+    assert torch.equal(plain.view(B, O, -1), want_plain)
