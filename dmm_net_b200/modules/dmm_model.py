@@ -117,3 +117,76 @@ class DMM_Model(nn.Module):
         loss = out['cost_loss'] * (n_tmpl > 0).float()       # videos without templates contribute prop_feat.sum()*0
         match_loss = list(loss.unbind(0))
         return output_mask, tplt_dict, match_loss, out_mask_last
+
+    # ------------------------------------------------------------------------------------------------------
+    def inference_lazy(self, infos, detections, backbone_feature, mask_last_occurence, tplt_dict, nms_thresh=0.8,
+                       max_proposals=50, mask_threshold=0.5, padding=1):
+        """``inference`` fed with the mask head's raw outputs instead of pasted masks (SURVEY.md 8f-2 + 8f-4 together).
+
+        The reference pastes every detection into a full-resolution soft mask (masker.py), runs NMS on the tight boxes
+        (boxlist_ops.py), then matches; per frame that writes P*HW*4 bytes, reads them for the IoU and reads the selected
+        ones again for ``torch.mm``.  The IoU only needs one bit per pixel and the apply only the <= O selected
+        detections, so here the soft masks are never materialised:
+          K8 (bits + tight boxes only) -> K9 NMS -> K5 features of the kept boxes -> K2 -> K1 on packed rows -> K3 ->
+          K10 pastes the selected detections, scaled, straight into the output rows.
+        No host synchronisation anywhere (the keep lists stay on the device as an index table).  Outputs are
+        bit-identical to ``Masker`` -> ``filter_results`` -> ``inference`` (tests/test_gpu_container.py).
+
+        detections: list (one per video) of BoxList-likes with ``bbox`` [n,4] (detector boxes), field ``mask`` [n,1,M,M]
+        (mask-head probabilities, NOT pasted) and ``scores`` / ``objectness`` [n].
+        Returns (output_mask [B,F,H,W], tplt_dict, [], out_mask_last, keep) -- ``keep`` = (index table [B,P], n_prop [B])."""
+        B, F, H, W = CHECK4D(mask_last_occurence)
+        CHECKEQ(len(detections), B)
+        dev = mask_last_occurence.device
+        counts = [len(d) for d in detections]
+        n_max = max(max(counts), 1)
+        m_all = torch.cat([d.get_field('mask').reshape(len(d), d.get_field('mask').shape[-2], d.get_field('mask').shape[-1])
+                           for d in detections], 0)
+        b_all = torch.cat([d.bbox for d in detections], 0).to(dev)
+        pasted = ops.paste_masks(m_all, b_all, H, W, mask_threshold, padding, want_pasted=False, want_bits=True)   # K8
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        tight = torch.zeros(B, n_max, 4, device=dev)
+        score = torch.zeros(B, n_max, device=dev)
+        for b, d in enumerate(detections):                       # fixed-size staging of the ragged lists (no sync)
+            tight[b, :counts[b]] = pasted['tight'][offs[b]:offs[b + 1]].float()
+            score[b, :counts[b]] = (d.get_field('objectness') if 'objectness' in d.fields() else d.get_field('scores')).float()
+        cnt = torch.tensor(counts, dtype=torch.int32, device=dev)
+        keep, n_keep = ops.box_nms(tight, score, nms_thresh, max_proposals, cnt)                                     # K9
+        P = n_max if max_proposals <= 0 else min(max_proposals, n_max)
+        keep = keep[:, :P]
+        n_prop = n_keep.clamp(max=P)
+        kept = keep >= 0
+        local = keep.clamp(min=0)
+        src_index = torch.where(kept, local + torch.tensor(offs[:-1], device=dev)[:, None], torch.full_like(local, -1)).to(torch.int32)
+        gidx = src_index.clamp(min=0).long()
+        rois = torch.cat([torch.arange(B, device=dev, dtype=torch.float32)[:, None, None].expand(B, P, 1),
+                          pasted['tight'][gidx].float()], 2).view(B * P, 5)
+        prop_feat = self.feature_extractor.pool_rois(backbone_feature, rois).view(B, P, -1)                          # K5
+        prop_bits = pasted['bits'][gidx]                                                                             # [B,P,words]
+        prop_score = torch.gather(score, 1, local) * kept
+        valid = infos['valid'].to(dev).float().view(B, -1)
+        CHECKEQ(valid.shape[1], F)
+        n_tmpl = valid.sum(1).round().to(torch.int32)
+        extra = infos.get('extra_frame')
+        if extra is not None:
+            n_tmpl = torch.where(torch.as_tensor(extra).bool().view(-1).to(dev), torch.zeros_like(n_tmpl), n_tmpl)
+        T = len(tplt_dict[0]['feat'])
+        tmpl_feat = torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)
+        tmpl_feat = tmpl_feat * valid[:, None, :, None]
+        ar = torch.arange(F, device=dev, dtype=torch.int32)[None, :].expand(B, -1)
+        row_map = torch.where(valid > 0, ar, torch.full_like(ar, -1)).contiguous()
+        layer = self.match_layer
+        with torch.no_grad():
+            cos = ops.cosine_pairwise(tmpl_feat, prop_feat, n_prop, n_tmpl)                                          # K2
+            w = float(layer.cfgs['score_weight'])
+            tmpl_bits = ops.pack_masks(mask_last_occurence.float(), mask_dims=2)                                     # [B,F,words]
+            r = ops.mask_iou_pairwise_packed(prop_bits.contiguous(), tmpl_bits, None, n_prop, n_tmpl, cos=cos,
+                                             w_cos=1 - w, w_iou=w)                                                   # K1 packed
+            _, Bm, _, _, _, _, _ = ops.relax_solve(r['sim'], prop_score, n_prop, n_tmpl, layer.max_iter, layer.proj_iter,
+                                                   layer.relax_lr, True, True, bool(layer.is_test))                  # K3
+            output_mask = ops.paste_apply(Bm, m_all, b_all, src_index, H, W, n_prop, n_tmpl, row_map, F, True, padding)   # K10
+        empty = (n_tmpl == 0).view(B, 1, 1, 1)
+        out_mask_last = torch.where(empty, mask_last_occurence.to(output_mask.dtype), output_mask)
+        return output_mask, tplt_dict, [], out_mask_last, (src_index, n_prop)

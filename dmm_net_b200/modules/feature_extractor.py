@@ -28,6 +28,12 @@ class FeatureExtractor(nn.Module):
             rows.append(torch.cat([ids, bb], dim=1))
         return rows[0] if len(rows) == 1 else torch.cat(rows, dim=0)
 
+    def pool_rois(self, backbone_feature, rois):
+        """rois [R,5] = (image index, x1, y1, x2, y2) already in ROI format -> [R, 4*C] (what ``forward`` computes after
+        ``convert_to_roi_format``); used by the lazy pipeline, whose kept boxes live in a fixed-size device table."""
+        assert len(backbone_feature) == self.num_levels, len(backbone_feature)
+        return ops.roi_mean_pool(list(backbone_feature), rois)
+
     def forward(self, backbone_feature, proposals):
         """backbone_feature: 4 tensors [B,C,H/s,W/s] (s = 4, 8, 16, 32); proposals: list of B BoxList-likes.
         Returns [sum_b len(proposals[b]), 4*C], level-major per ROI like ``result.mean(4).mean(3).view(R,-1)`` (:20-30)."""

@@ -90,16 +90,24 @@ def run(args):
             n_raw = args.proposals + 14                              # detections before NMS
             raw = [BoxList(random_boxes(gen, n_raw, H, W, dev), (W, H)) for _ in range(B)]
             m28 = [torch.sigmoid(3 * torch.randn(n_raw, 1, 28, 28, generator=gen, device=dev) + 1.5) for _ in range(B)]
-            pasted, tight = masker(m28, raw)                         # K8: all B x n_raw proposals in one launch
-            props = []
-            for b in range(B):
-                bl = BoxList(tight[b].float(), (W, H))               # mask post-processor: boxes become the tight boxes
-                bl.add_field("mask", pasted[b])
-                bl.add_field("scores", torch.rand(n_raw, generator=gen, device=dev))
-                props.append(bl)
-            props = filter_results(props, nms_thresh=0.8, max_proposals=args.proposals)      # K9: one launch per frame
+            scores = [torch.rand(n_raw, generator=gen, device=dev) for _ in range(B)]
             prev = mask_last
-            out, tplt, _, mask_last = model.inference(infos, props, fb, mask_last, tplt)
+            if args.lazy:
+                # lazy pipeline: bits-only paste, device-side keep table, packed K1, K10 pastes only the matched detections
+                for b in range(B):
+                    raw[b].add_field("mask", m28[b])
+                    raw[b].add_field("scores", scores[b])
+                out, tplt, _, mask_last, _ = model.inference_lazy(infos, raw, fb, mask_last, tplt, 0.8, args.proposals)
+            else:
+                pasted, tight = masker(m28, raw)                     # K8: all B x n_raw proposals in one launch
+                props = []
+                for b in range(B):
+                    bl = BoxList(tight[b].float(), (W, H))           # mask post-processor: boxes become the tight boxes
+                    bl.add_field("mask", pasted[b])
+                    bl.add_field("scores", scores[b])
+                    props.append(bl)
+                props = filter_results(props, nms_thresh=0.8, max_proposals=args.proposals)  # K9: one launch per frame
+                out, tplt, _, mask_last = model.inference(infos, props, fb, mask_last, tplt)
             levels = ops.mask_pyramid(prev, mask0, out, 4)           # K6: decoder inputs of every object (identity decoder here)
             labels = ops.merge_labels(out.view(B, F, -1), n_obj)     # K7: merged label map (evaluator.py:139-145)
             checks.append(float(out.sum()) + float(levels[-1].sum()) + float(labels.sum()))
@@ -112,7 +120,7 @@ def run(args):
     assert labels.shape == (B, H * W) and int(labels.max()) <= F and levels[0].shape == (F, B, 3, (H + 3) // 4, (W + 3) // 4)
     assert float((out * (1 - valid)[:, :, None, None]).abs().sum()) == 0.0, "rows of invalid templates must stay zero"
     if rank == 0:
-        print(f"clips={args.clips} ranks={world} frames/clip={args.frames} P~{args.proposals} F={F} {H}x{W}: "
+        print(f"{'lazy' if args.lazy else 'paste-all'} pipeline: clips={args.clips} ranks={world} frames/clip={args.frames} P~{args.proposals} F={F} {H}x{W}: "
               f"{rate:.0f} (clip,frame) matches/s incl. paste + NMS + pyramid + labels; last checksum {checks[-1]:.3f}")
     if world > 1:
         dist.destroy_process_group()
@@ -126,4 +134,5 @@ if __name__ == "__main__":
     ap.add_argument("--proposals", type=int, default=50)
     ap.add_argument("--objects", type=int, default=5)
     ap.add_argument("--size", type=int, nargs=2, default=[256, 448])
+    ap.add_argument("--lazy", action="store_true", help="never materialise the pasted proposal masks (DMM_Model.inference_lazy)")
     run(ap.parse_args())

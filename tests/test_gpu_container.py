@@ -148,8 +148,9 @@ def test_synthetic_clip_loop_runs_sequential_frames():
     spec = importlib.util.spec_from_file_location("synthetic_clip_eval", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    rate = mod.run(argparse.Namespace(clips=3, frames=4, proposals=9, objects=3, size=[64, 96]))
+    rate = mod.run(argparse.Namespace(clips=3, frames=4, proposals=9, objects=3, size=[64, 96], lazy=False))
     assert rate > 0
+    assert mod.run(argparse.Namespace(clips=3, frames=4, proposals=9, objects=3, size=[64, 96], lazy=True)) > 0
 
 
 def test_synthetic_train_step_runs_and_produces_gradients():
@@ -164,3 +165,52 @@ def test_synthetic_train_step_runs_and_produces_gradients():
     spec.loader.exec_module(mod)
     hist = mod.run(argparse.Namespace(steps=3, clips=2, frames=3, objects=2, proposals=7, arch="resnet18", size=[64, 96]))
     assert len(hist) == 3 and all(h[0] == h[0] for h in hist)
+
+
+def test_lazy_pipeline_is_bit_identical_to_paste_nms_match():
+    """DMM_Model.inference_lazy (bits-only paste, device-side keep table, packed K1, fused paste+apply) ==
+    Masker -> filter_results -> DMM_Model.inference, frame after frame (the outputs feed the next frame's templates)."""
+    from dmm_net_b200.utils.boxlist_ops import filter_results
+    from dmm_net_b200.utils.masker import Masker
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    B, F, H, W, C, n_det, P = 3, 4, 64, 96, 16, [23, 17, 30], 12
+    model = DMM_Model(default_cfg(20, 5), is_test=1).to(DEV)
+    valid = torch.tensor([[1, 1, 1, 0], [1, 0, 0, 0], [1, 1, 1, 1]], device=DEV).float()
+    feats = lambda: tuple(torch.randn(B, C, H // s, W // s, generator=gen, device=DEV) for s in (4, 8, 16, 32))
+
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=gen, device=DEV) * torch.tensor([W * 0.6, H * 0.6], device=DEV)
+        wh = torch.rand(n, 2, generator=gen, device=DEV) * torch.tensor([W * 0.4, H * 0.4], device=DEV) + 4
+        return torch.cat([xy, (xy + wh).clamp(max=min(H, W) - 1)], 1)
+
+    f0 = feats()
+    tb = [boxes(F) for _ in range(B)]
+    tplt = model.fill_template_dict(None, [BoxList(b) for b in tb], {"backbone_feature": f0, "refine_input_feat": f0}, None, valid)
+    masker = Masker(0.5, 1)
+    m0, _ = masker([torch.ones(F, 1, 28, 28, device=DEV)] * B, [BoxList(b, (W, H)) for b in tb])
+    last_a = last_b = torch.stack([m.squeeze(1) for m in m0], 0) * valid[:, :, None, None]
+    infos = {"args": None, "shape": (H, W), "extra_frame": [0, 0, 0], "valid": valid}
+    for t in range(3):
+        fb = feats()
+        dets = []
+        for b in range(B):
+            d = BoxList(boxes(n_det[b]), (W, H))
+            d.add_field("mask", torch.sigmoid(3 * torch.randn(n_det[b], 1, 28, 28, generator=gen, device=DEV) + 1))
+            d.add_field("scores", (torch.rand(n_det[b], generator=gen, device=DEV) * 10).round() / 10)   # tied scores
+            dets.append(d)
+        # reference-shaped path: paste everything, NMS on the tight boxes, match
+        pasted, tight = masker([d.get_field("mask") for d in dets], dets)
+        props = []
+        for b, d in enumerate(dets):
+            bl = BoxList(tight[b].float(), (W, H))
+            bl.add_field("mask", pasted[b])
+            bl.add_field("scores", d.get_field("scores"))
+            props.append(bl)
+        props = filter_results(props, nms_thresh=0.8, max_proposals=P)
+        with torch.no_grad():
+            out_a, _, _, last_a = model.inference(infos, props, fb, last_a, tplt)
+            out_b, _, _, last_b, (src_index, n_prop) = model.inference_lazy(infos, dets, fb, last_b, tplt, 0.8, P)
+        assert n_prop.tolist() == [len(p) for p in props]
+        assert torch.equal(out_a, out_b), t
+        assert torch.equal(last_a, last_b), t
+        assert float(out_a.abs().sum()) > 0
