@@ -77,9 +77,7 @@ class DMM_Model(nn.Module):
         if skip is not None:
             n_tmpl = torch.where(skip.to(dev), torch.zeros_like(n_tmpl), n_tmpl)
         # reference semantics: rows :O of diag(valid) -> row i is valid[i]*e_i (dmm_model.py:152-154)
-        T = len(tplt_dict[0]['feat'])
-        tmpl_feat = torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)  # [B,T,F,D]
-        tmpl_feat = tmpl_feat * valid[:, None, :, None]
+        tmpl_feat = self._stacked_templates(tplt_dict, B) * valid[:, None, :, None]                  # [B,T,F,D]
         ar = torch.arange(Fm, device=dev, dtype=torch.int32)[None, :].expand(B, -1)
         row_map = torch.where(valid > 0, ar, torch.full_like(ar, -1)).contiguous()      # scatter fused into K4
         n_prop = torch.tensor(boxes_per_image, dtype=torch.int32, device=dev)
@@ -118,6 +116,21 @@ class DMM_Model(nn.Module):
         match_loss = list(loss.unbind(0))
         return output_mask, tplt_dict, match_loss, out_mask_last
 
+    def _stacked_templates(self, tplt_dict, B):
+        """[B,T,F,D] stack of the per-video template features; the dict does not change between the frames of a clip, so
+        the stack is cached on the identity of its tensors instead of being rebuilt (B small copies) every frame."""
+        T = len(tplt_dict[0]['feat'])
+        if torch.is_grad_enabled() and any(tplt_dict[b]['feat'][t].requires_grad for b in range(B) for t in range(T)):
+            # training: every frame gets its own stack node in the autograd graph, like the reference's per-frame rebuild
+            return torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)
+        key = tuple(id(tplt_dict[b]['feat'][t]) for b in range(B) for t in range(T))
+        cached = getattr(self, '_tmpl_cache', None)
+        if cached is None or cached[0] != key:
+            stacked = torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)
+            cached = (key, stacked, [tplt_dict[b]['feat'] for b in range(B)])      # keeps the tensors (and their ids) alive
+            self._tmpl_cache = cached
+        return cached[1]
+
     # ------------------------------------------------------------------------------------------------------
     def inference_lazy(self, infos, detections, backbone_feature, mask_last_occurence, tplt_dict, nms_thresh=0.8,
                        max_proposals=50, mask_threshold=0.5, padding=1):
@@ -147,11 +160,15 @@ class DMM_Model(nn.Module):
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + c)
-        tight = torch.zeros(B, n_max, 4, device=dev)
-        score = torch.zeros(B, n_max, device=dev)
-        for b, d in enumerate(detections):                       # fixed-size staging of the ragged lists (no sync)
-            tight[b, :counts[b]] = pasted['tight'][offs[b]:offs[b + 1]].float()
-            score[b, :counts[b]] = (d.get_field('objectness') if 'objectness' in d.fields() else d.get_field('scores')).float()
+        sc_all = torch.cat([(d.get_field('objectness') if 'objectness' in d.fields() else d.get_field('scores')).float()
+                            for d in detections], 0)
+        if all(c == n_max for c in counts):                      # equal counts: the flat lists already are the [B, n] tables
+            tight = pasted['tight'].float().view(B, n_max, 4)
+            score = sc_all.view(B, n_max)
+        else:                                                    # ragged: ONE scatter through a host-built index (no sync)
+            flat = torch.tensor([b * n_max + j for b, c in enumerate(counts) for j in range(c)], dtype=torch.long).to(dev)
+            tight = torch.zeros(B * n_max, 4, device=dev).index_copy_(0, flat, pasted['tight'].float()).view(B, n_max, 4)
+            score = torch.zeros(B * n_max, device=dev).index_copy_(0, flat, sc_all).view(B, n_max)
         cnt = torch.tensor(counts, dtype=torch.int32, device=dev)
         keep, n_keep = ops.box_nms(tight, score, nms_thresh, max_proposals, cnt)                                     # K9
         P = n_max if max_proposals <= 0 else min(max_proposals, n_max)
@@ -172,9 +189,7 @@ class DMM_Model(nn.Module):
         extra = infos.get('extra_frame')
         if extra is not None:
             n_tmpl = torch.where(torch.as_tensor(extra).bool().view(-1).to(dev), torch.zeros_like(n_tmpl), n_tmpl)
-        T = len(tplt_dict[0]['feat'])
-        tmpl_feat = torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)
-        tmpl_feat = tmpl_feat * valid[:, None, :, None]
+        tmpl_feat = self._stacked_templates(tplt_dict, B) * valid[:, None, :, None]
         ar = torch.arange(F, device=dev, dtype=torch.int32)[None, :].expand(B, -1)
         row_map = torch.where(valid > 0, ar, torch.full_like(ar, -1)).contiguous()
         layer = self.match_layer
