@@ -17,7 +17,6 @@ builds the decoder's mask-input pyramid for every object and K7 merges the outpu
 import argparse
 import os
 import sys
-import time
 
 import torch
 

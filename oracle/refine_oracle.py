@@ -4,14 +4,14 @@ Same rules as ``oracle/match_oracle.py``: torch-CPU fp32 restatement of the refe
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs; never by the product path.
 
 Parity status
-  mask_pyramid, merged_labels   PINNED: ``oracle/make_golden.py`` executes the reference's own source lines
+  mask_pyramid, merged_labels   PINNED: ``oracle/make_golden_refine.py`` executes the reference's own source lines
                                 (dmm/modules/trainer.py:256-263, dmm/modules/evaluator.py:139-145, read from
                                 /root/reference at generation time) on seeded inputs and stores what they produced
-                                under ``tests/golden/refine_*.npz``; ``tests/test_oracle_golden.py`` holds this file to them.
+                                under ``tests/golden/refine_*.npz``; ``tests/test_refine_rows.py`` holds this file to them.
   paste_masks                   PINNED: the reference's ``dmm.utils.masker.paste_mask_in_image`` is imported (with the
                                 un-vendored ``maskrcnn_benchmark`` names it pulls in stubbed: ``interpolate`` is
                                 ``torch.nn.functional.interpolate``, which is what that wrapper forwards to) and its
-                                outputs stored in ``tests/golden/paste_*.npz``.
+                                outputs stored in ``tests/golden/paste_*.npz`` (``tests/test_paste_nms.py``: reproduced bit for bit).
   box_nms                       parity UNPINNED: the arithmetic lives in the un-vendored ``maskrcnn_benchmark.layers.nms``
                                 (fork without a pinned commit, INSTALL.md:19-39); restated from its published algorithm
                                 (greedy, score-descending, IoU with the legacy +1 pixel widths, suppress when IoU > thresh).
@@ -25,7 +25,7 @@ Reference lines restated:
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List
 
 import torch
 import torch.nn.functional as F

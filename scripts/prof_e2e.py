@@ -2,7 +2,6 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from dmm_net_b200 import ops
 from dmm_net_b200.modules.match_model import MatchModel
 from dmm_net_b200.synth import default_cfg, make_problems
 

@@ -1,14 +1,12 @@
 """The plain-C integer oracle (oracle/iou_oracle.c) against the torch-CPU oracle, the reference's golden vectors, the host
 packer and -- on the GPU -- K1's counts.  Three independent implementations of the same integers must agree exactly."""
 import ctypes
-import os
-import subprocess
 
 import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, golden_names, load_golden
+from conftest import golden_names, load_golden
 from dmm_net_b200 import ops
 from dmm_net_b200.synth import make_problem
 from oracle import match_oracle as orc
