@@ -54,6 +54,8 @@ def main():
             print(f"K8 paste N={N}: {ms*1e3:.1f} us  {N*H*W*4/ms/1e6:.0f} GB/s written")
             ms = timeit(lambda: ops.paste_masks(masks, boxes, H, W, want_bits=True))
             print(f"K8 paste+bits N={N}: {ms*1e3:.1f} us")
+            ms = timeit(lambda: ops.paste_masks(masks, boxes, H, W, want_pasted=False, want_bits=True))
+            print(f"K8 bits + tight boxes only N={N}: {ms*1e3:.1f} us")
 
 
 if __name__ == "__main__":
