@@ -18,6 +18,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kRes = 14;       // feature_extractor.py:15
 constexpr int kSamp = 2;       // feature_extractor.py:14
 constexpr int kNS = kRes * kSamp;
+constexpr int kTabCap = 2048;  // window cells per forward table chunk
 
 struct PoolParams {
   const float* feat[4];
@@ -80,10 +81,14 @@ __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParam
   axis_range(y1, y2, H, scale, ya, yb);
   axis_range(x1, x2, W, scale, xa, xb);
   const int ww = xb - xa + 1, hh = yb - ya + 1, cnt = ww * hh;
+  // Forward: the table holds at most kTabCap window cells at a time (16 KB: 8 CTAs per SM instead of the 3 that a table
+  // sized for the whole level-0 map allowed); larger windows are walked in chunks.  Backward keeps the full-map table.
+  const int tab_cap = BWD ? H * W : kTabCap;
   int* toff = reinterpret_cast<int*>(wsm + H + W);
-  float* tw = wsm + H + W + (TABLE ? H * W : 0);
+  float* tw = wsm + H + W + (TABLE ? tab_cap : 0);
   __syncthreads();
-  if (TABLE) {
+  const bool valid = n >= 0 && n < p.N;
+  if (TABLE && BWD) {
     for (int i = tid; i < cnt; i += kThreads) {
       const int y = ya + i / ww, x = xa + i % ww;
       toff[i] = y * W + x;
@@ -91,23 +96,42 @@ __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParam
     }
     __syncthreads();
   }
-  const bool valid = n >= 0 && n < p.N;
   if (!BWD) {
     float* o = p.out + (long long)r * 4 * p.C + (long long)l * p.C;
-    for (int c = warp; c < p.C; c += kWarps) {
-      float acc = 0.f;
-      if (valid) {
-        const float* f = p.feat[l] + ((long long)n * p.C + c) * H * W;
-        if (TABLE) {
-          float a0 = 0.f, a1 = 0.f;
-          int i = lane;
-          for (; i + 32 < cnt; i += 64) {
-            a0 = fmaf(tw[i], __ldg(f + toff[i]), a0);
-            a1 = fmaf(tw[i + 32], __ldg(f + toff[i + 32]), a1);
+    if (TABLE) {
+      for (int base = 0; base == 0 || base < cnt; base += kTabCap) {
+        const int m = min(kTabCap, cnt - base);
+        if (base > 0) __syncthreads();                       // previous chunk consumed by every warp
+        for (int i = tid; i < m; i += kThreads) {
+          const int idx = base + i, y = ya + idx / ww, x = xa + idx % ww;
+          toff[i] = y * W + x;
+          tw[i] = wy[y] * wx[x];
+        }
+        __syncthreads();
+        for (int c = warp; c < p.C; c += kWarps) {
+          float acc = 0.f;
+          if (valid) {
+            const float* f = p.feat[l] + ((long long)n * p.C + c) * H * W;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;    // four gathers in flight per lane: the loop is L2-latency bound
+            int i = lane;
+            for (; i + 96 < m; i += 128) {
+              const float v0 = __ldg(f + toff[i]), v1 = __ldg(f + toff[i + 32]);
+              const float v2 = __ldg(f + toff[i + 64]), v3 = __ldg(f + toff[i + 96]);
+              a0 = fmaf(tw[i], v0, a0); a1 = fmaf(tw[i + 32], v1, a1);
+              a2 = fmaf(tw[i + 64], v2, a2); a3 = fmaf(tw[i + 96], v3, a3);
+            }
+            for (; i < m; i += 32) a0 = fmaf(tw[i], __ldg(f + toff[i]), a0);
+            acc = (a0 + a1) + (a2 + a3);
           }
-          if (i < cnt) a0 = fmaf(tw[i], __ldg(f + toff[i]), a0);
-          acc = a0 + a1;
-        } else {
+          acc = warp_sum(acc);
+          if (lane == 0) o[c] = base == 0 ? acc : o[c] + acc;
+        }
+      }
+    } else {
+      for (int c = warp; c < p.C; c += kWarps) {
+        float acc = 0.f;
+        if (valid) {
+          const float* f = p.feat[l] + ((long long)n * p.C + c) * H * W;
           for (int y = ya; y <= yb; ++y) {
             const float wyv = wy[y];
             if (wyv == 0.f) continue;
@@ -116,9 +140,9 @@ __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParam
             acc = fmaf(wyv, rowacc, acc);
           }
         }
+        acc = warp_sum(acc);
+        if (lane == 0) o[c] = acc;
       }
-      acc = warp_sum(acc);
-      if (lane == 0) o[c] = acc;
     }
   } else {
     if (!valid) return;
@@ -160,7 +184,7 @@ static int fill(PoolParams& kp, const int Hl[4], const int Wl[4], int N, int C, 
     const size_t need = (size_t)(Hl[l] + Wl[l]) * sizeof(float) + (size_t)Hl[l] * Wl[l] * 8;
     if (need > tab) tab = need;
   }
-  table_smem = tab <= 200 * 1024 ? tab : 0;   // 0: feature maps too large for the window table -> index math path
+  table_smem = tab <= 200 * 1024 ? tab : 0;   // backward; 0: feature maps too large for the window table -> index math path
   kp.N = N; kp.C = C; kp.R = R; kp.rois = rois; kp.out = nullptr; kp.gout = nullptr;
   return DMM_OK;
 }
@@ -174,12 +198,11 @@ extern "C" int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], co
   if (!feat || !rois || !out) return DMM_ERR_INVALID_ARGUMENT;
   for (int l = 0; l < 4; ++l) { if (!feat[l]) return DMM_ERR_INVALID_ARGUMENT; kp.feat[l] = feat[l]; }
   kp.out = out;
-  if (tsmem) {
-    DMM_CUDA_TRY(cudaFuncSetAttribute(roi_mean_pool_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-    roi_mean_pool_kernel<false, true><<<dim3(R, 4), kThreads, tsmem, (cudaStream_t)stream>>>(kp);
-  } else {
-    roi_mean_pool_kernel<false, false><<<dim3(R, 4), kThreads, smem, (cudaStream_t)stream>>>(kp);
-  }
+  (void)tsmem;
+  const size_t fsmem = smem + (size_t)kTabCap * 8;            // wy, wx + one table chunk: ~17 KB, 8 CTAs per SM
+  if (fsmem > 48 * 1024)
+    DMM_CUDA_TRY(cudaFuncSetAttribute(roi_mean_pool_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  roi_mean_pool_kernel<false, true><<<dim3(R, 4), kThreads, fsmem, (cudaStream_t)stream>>>(kp);
   return check_launch();
 }
 
