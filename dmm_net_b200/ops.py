@@ -926,13 +926,15 @@ def _fold_route_measurement(key):
         _HOST_PENDING[key] = pend
         return
     old = _HOST_SPLIT.get(key)
-    new_pack = t_host / npk if npk >= max(4, B // 8) else None
-    new_dma = e0.elapsed_time(ev_dma) * 1e-3 / nraw if nraw >= max(4, B // 8) else None
+    new_pack = t_host / npk if npk >= max(1, B // 8) else None
+    new_dma = e0.elapsed_time(ev_dma) * 1e-3 / nraw if nraw >= max(1, B // 8) else None
     if old is None:
         if new_pack is not None and new_dma is not None:
             _HOST_SPLIT[key] = (new_pack, new_dma)
         return
-    mix = lambda o, n: o if n is None else 0.5 * (o + n)
+    # one slow sample (a copy queued behind another rank's traffic, a throttled packing burst) must not swing the split:
+    # a sample counts at most as 3x the current estimate
+    mix = lambda o, n: o if n is None else 0.5 * (o + min(n, 3.0 * o))
     _HOST_SPLIT[key] = (mix(old[0], new_pack), mix(old[1], new_dma))
 
 
@@ -977,7 +979,8 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
         est = _HOST_SPLIT.get(key)
         # first call: nominal 100 GB/s of packing against 50 GB/s of PCIe; afterwards the measured rates
         t_pack, t_dma = est if est else (1.0, 2.0)
-        raw_fraction = min(0.9, t_pack / (t_pack + t_dma))
+        # both routes always carry at least an eighth of the batch, so that both keep being measured
+        raw_fraction = min(0.875, max(0.125, t_pack / (t_pack + t_dma)))
     nraw = int(round(B * float(raw_fraction))) if can_raw and B >= 4 else 0
     nraw = max(0, min(nraw, B))
     main = torch.cuda.current_stream(dev)
@@ -987,9 +990,12 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     if nraw > 0:
         copy_stream = _side_streams(dev)[0]                    # not ordered after `main`: the DMA may start while the previous
         with torch.cuda.stream(copy_stream):                   # call's kernels still run (fresh buffers, read-only source)
+            pm_raw = torch.empty((nraw, P, HW), device=dev)    # allocate first: a cudaMalloc inside the timed pair would
+            tm_raw = torch.empty((nraw, O, HW), device=dev)    # be booked as DMA time
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            pm_raw, tm_raw = to_dev(prop_mask[:nraw]), to_dev(tmpl_mask[:nraw])
+            pm_raw.copy_(prop_mask[:nraw], non_blocking=True)
+            tm_raw.copy_(tmpl_mask[:nraw], non_blocking=True)
             ev_dma = torch.cuda.Event(enable_timing=True)
             ev_dma.record()
     npk = B - nraw
