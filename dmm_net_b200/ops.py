@@ -972,7 +972,7 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     th = host_threads() if threads is None else int(threads)
     prop_mask = prop_mask.reshape(B, P, HW)
     tmpl_mask = tmpl_mask.reshape(B, O, HW)
-    key = (P, O, HW)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), P, O, HW)   # per device: one thread per GPU
     can_raw = prop_mask.is_pinned() and tmpl_mask.is_pinned() and prop_mask.is_contiguous() and tmpl_mask.is_contiguous()
     _fold_route_measurement(key)
     if raw_fraction is None:
@@ -1006,7 +1006,8 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
         # not overwrite bits that are still being copied.  The event of a slot is waited for before the slot is reused.
         slot = _STAGE_TURN.get(key, 0)
         _STAGE_TURN[key] = slot ^ 1
-        pb_full, tb_full = _pinned(("pb", slot), (B, P, words), torch.int32), _pinned(("tb", slot), (B, O, words), torch.int32)
+        pb_full = _pinned(("pb", key[0], slot), (B, P, words), torch.int32)
+        tb_full = _pinned(("tb", key[0], slot), (B, O, words), torch.int32)
         busy = _STAGE_EVENT.get((key, slot))
         if busy is not None:
             busy.synchronize()
