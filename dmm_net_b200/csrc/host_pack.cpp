@@ -8,8 +8,8 @@
 #include <stddef.h>
 
 #include <atomic>
+#include <functional>
 #include <thread>
-#include <vector>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -114,11 +114,17 @@ int pack_jobs(const PackJob* jobs, int njobs, long long HW, int threads) {
       }
     }
   };
-  std::vector<std::thread> pool;
-  pool.reserve((size_t)nt);
-  for (long long i = 1; i < nt; ++i) pool.emplace_back(work);
-  work();
-  for (auto& th : pool) th.join();
+  // The team starts as a binary tree (thread i starts 2i+1 and 2i+2 before it works): the last of 16 threads is running
+  // after 4 thread creations instead of 15, which matters when the whole call is ~10 ms.
+  std::function<void(long long)> run = [&](long long id) {
+    std::thread c1, c2;
+    if (2 * id + 1 < nt) c1 = std::thread(run, 2 * id + 1);
+    if (2 * id + 2 < nt) c2 = std::thread(run, 2 * id + 2);
+    work();
+    if (c1.joinable()) c1.join();
+    if (c2.joinable()) c2.join();
+  };
+  run(0);
   return DMM_OK;
 }
 
