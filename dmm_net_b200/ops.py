@@ -975,16 +975,22 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), P, O, HW)   # per device: one thread per GPU
     can_raw = prop_mask.is_pinned() and tmpl_mask.is_pinned() and prop_mask.is_contiguous() and tmpl_mask.is_contiguous()
     _fold_route_measurement(key)
+    auto_split = raw_fraction is None
     if raw_fraction is None:
         est = _HOST_SPLIT.get(key)
         # first call: nominal 100 GB/s of packing against 50 GB/s of PCIe; afterwards the measured rates
         t_pack, t_dma = est if est else (1.0, 2.0)
-        # both routes always carry at least an eighth of the batch, so that both keep being measured
-        raw_fraction = min(0.875, max(0.125, t_pack / (t_pack + t_dma)))
+        # The raw route should finish a little BEFORE the packing does: the bit rows cross PCIe behind it on the same copy
+        # engine and the device work of the call starts only when both have landed -> weigh the packing time by 0.85.
+        # Both routes always carry at least an eighth of the batch, so that both keep being measured.
+        raw_fraction = min(0.875, max(0.125, 0.85 * t_pack / (0.85 * t_pack + t_dma)))
     nraw = int(round(B * float(raw_fraction))) if can_raw and B >= 4 else 0
+    if auto_split and B >= 32:
+        nraw = (nraw + 2) // 4 * 4                               # few distinct staging sizes: the allocator reuses its blocks
     nraw = max(0, min(nraw, B))
     main = torch.cuda.current_stream(dev)
     to_dev = lambda t: t.to(dev, non_blocking=True)
+    t_call = time.perf_counter()
     pm_raw = tm_raw = None
     ev_dma = None
     if nraw > 0:
@@ -1000,6 +1006,7 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
             ev_dma.record()
     npk = B - nraw
     t_host = 0.0
+    t_raw_enqueued = time.perf_counter() - t_call
     if npk > 0:
         # Pinned staging buffers, sized for the whole batch (the split moves from call to call; re-pinning would cost more)
         # and double-buffered: callers may issue the next call before this call's H2D has drained, and the packer must
@@ -1027,16 +1034,17 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     with torch.no_grad():
         cos = cosine_pairwise(tf, pf, n_prop, n_tmpl)
         w = float(score_weight)
-        parts = []
+        parts = [None, None]
+        if npk > 0:                                              # packed rows first: they do not wait for the raw DMA
+            parts[1] = mask_iou_pairwise_packed(pbd, tbd, None, sl(n_prop, nraw, B), sl(n_tmpl, nraw, B), cos=cos[nraw:],
+                                                w_cos=1 - w, w_iou=w)
         if nraw > 0:
             main.wait_event(ev_dma)
             pm_raw.record_stream(main)
             tm_raw.record_stream(main)
-            parts.append(mask_iou_pairwise(pm_raw, tm_raw, None, sl(n_prop, 0, nraw), sl(n_tmpl, 0, nraw), cos=cos[:nraw],
-                                           w_cos=1 - w, w_iou=w))
-        if npk > 0:
-            parts.append(mask_iou_pairwise_packed(pbd, tbd, None, sl(n_prop, nraw, B), sl(n_tmpl, nraw, B), cos=cos[nraw:],
-                                                  w_cos=1 - w, w_iou=w))
+            parts[0] = mask_iou_pairwise(pm_raw, tm_raw, None, sl(n_prop, 0, nraw), sl(n_tmpl, 0, nraw), cos=cos[:nraw],
+                                         w_cos=1 - w, w_iou=w)
+        parts = [q for q in parts if q is not None]
         if len(parts) == 1:
             iou, sim = parts[0]["iou"], parts[0]["sim"]
         else:
@@ -1053,4 +1061,5 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     return {"cos": cos, "iou": iou, "sim": sim, "R": R, "Bmat": Bm, "logic": logic, "X_final": Xf,
             "match_score": ms, "det_score": ds, "n_list": n_list, "h2d_bytes": h2d,
             "host_packed_bytes": 4 * npk * (P + O) * HW, "host_threads": th, "raw_problems": nraw, "packed_problems": npk,
-            "host_pack_seconds": t_host, "route_estimate": _HOST_SPLIT.get(key)}
+            "host_pack_seconds": t_host, "route_estimate": _HOST_SPLIT.get(key),
+            "host_seconds": {"enqueue_raw_route": t_raw_enqueued, "pack": t_host, "whole_call": time.perf_counter() - t_call}}
