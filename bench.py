@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="independent problems per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (rank 0, N=1)")
-    ap.add_argument("--e2e-steps", type=int, default=20, help="timed host-buffer steps (the pipeline drain at the end is amortised over them)")
+    ap.add_argument("--e2e-steps", type=int, default=40, help="timed host-buffer steps (the pipeline drain at the end is amortised over them)")
     ap.add_argument("--secondary-steps", type=int, default=5, help="timed steps of the full-layer secondary metric (0: skip)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads for mask packing (0: cgroup-aware default)")
     args = ap.parse_args()
