@@ -39,6 +39,13 @@ __device__ __forceinline__ bool takes(float cur, float nxt) { return nxt > cur |
 
 struct VI { float v; int i; };
 __device__ __forceinline__ VI fold(VI a, VI b) { return takes(a.v, b.v) ? b : a; }
+// Forward needs values only: max.NaN.f32 is ATen's rule in one instruction (NaN wins; the larger value otherwise).  The
+// forward kernel was issue-bound (ncu: 80 % issue slots busy at 64 % DRAM) on the compare/select pairs of `fold`.
+__device__ __forceinline__ float vmax(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 
 template <bool VEC>
 __device__ __forceinline__ void load_patch(const float* plane, int H, int W, int y0, int x0, float (&v)[4][4]) {
@@ -95,14 +102,28 @@ __global__ void __launch_bounds__(kThreads) mask_pyramid_kernel(const PyrParams 
   const int y0 = tile_y * kTile + 4 * ty, x0 = tile_x * kTile + 4 * tx;
   float v[4][4];
   load_patch<VEC>(plane, p.H, p.W, y0, x0, v);
-  const VI m0 = pool_patch(v, ty, tx);
-  sv[tid] = m0.v;
-  if (BWD) si[tid] = m0.i;
+  if constexpr (BWD) {
+    const VI m0 = pool_patch(v, ty, tx);
+    sv[tid] = m0.v;
+    si[tid] = m0.i;
+  } else {
+    float m = v[0][0];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) m = vmax(m, v[r][c]);
+    sv[tid] = m;
+  }
   __syncthreads();
   // levels 1.. : 64, 16, 4, 1 cells, each the row-major fold of a 2x2 block of the level below
   for (int k = 1; k < p.L; ++k) {
     const int n = 16 >> k;                      // cells per side at level k
-    if (tid < n * n) {
+    if (!BWD && tid < n * n) {
+      const int cy = tid / n, cx = tid % n, lo = lvl_off(k - 1), ns = 2 * n;
+      sv[lvl_off(k) + tid] = vmax(vmax(sv[lo + (2 * cy) * ns + 2 * cx], sv[lo + (2 * cy) * ns + 2 * cx + 1]),
+                                  vmax(sv[lo + (2 * cy + 1) * ns + 2 * cx], sv[lo + (2 * cy + 1) * ns + 2 * cx + 1]));
+    }
+    if (BWD && tid < n * n) {
       const int cy = tid / n, cx = tid % n, lo = lvl_off(k - 1), ns = 2 * n;
       VI m = {sv[lo + (2 * cy) * ns + 2 * cx], BWD ? si[lo + (2 * cy) * ns + 2 * cx] : 0};
       m = fold(m, VI{sv[lo + (2 * cy) * ns + 2 * cx + 1], BWD ? si[lo + (2 * cy) * ns + 2 * cx + 1] : 0});
