@@ -126,20 +126,47 @@ def tune_cpu_threads(one):
     return best
 
 
-def cpu_reference_rate(seconds_budget: float, threads: int):
-    """The reference's CPU path (oracle port: same torch-CPU op sequence incl. the [O*P,HW] expansions) on this
-    host's cores: cost-build + solve of the headline problem, timed one problem at a time."""
-    from oracle import match_oracle as orc
-    from dmm_net_b200.synth import make_problem
-    torch.set_num_threads(threads)
+CONFIG = {"workload": WORKLOAD, "inputs": "synthetic, seeded (dmm_net_b200/synth.py): fp32 soft masks, N(0,1) features"}
+
+
+def reference_callable():
+    """The CPU arm: one cost-build + solve of the headline problem per call.
+
+    kind "reference": the UNMODIFIED reference code (oracle/_ref = the four hot-path files copied from the reference tree by
+    oracle/build_ref.py at build time) -- MatchModel.compute_cost_matrix (match_model.py:49-91) followed by relax_matching
+    (relax_match.py:36-105), exactly what MatchModel.forward runs before the assignment-apply.
+    kind "port": oracle/match_oracle.py, used only when oracle/_ref is not there."""
+    from dmm_net_b200.synth import default_cfg, make_problem
     pr = make_problem(P, O, H, W, D, config=2, index=0)
+    try:
+        from oracle import build_ref
+        have_ref = build_ref.verify()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        MatchModel, relax_matching, _ = build_ref.import_reference()
+        layer = MatchModel(default_cfg(MAX_ITER, PROJ_ITER, LR, SCORE_W), is_test=1)
+        feats = {"proposed": pr.prop_feat, "template": [pr.tmpl_feat]}
+        masks = {"proposed": pr.prop_mask, "template": pr.tmpl_mask}
+        scores = {"proposal_score": pr.prop_score}
+
+        def one():
+            with torch.no_grad():
+                sim, _, _, _ = layer.compute_cost_matrix(feats, masks, scores, None)
+                return relax_matching(-sim, max_iter=MAX_ITER, proj_iter=PROJ_ITER, lr=LR)[2]
+        return one, "reference", "unmodified reference (oracle/_ref: MatchModel.compute_cost_matrix + relax_matching)"
+    from oracle import match_oracle as orc
 
     def one():
         with torch.no_grad():
             sim, _ = orc.cost_matrix(pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, SCORE_W, None, expand=True)
-            _, _, X_list, _ = orc.relax_solve(-sim, MAX_ITER, PROJ_ITER, LR)
-            return sum(X_list) / len(X_list)
+            return orc.relax_solve(-sim, MAX_ITER, PROJ_ITER, LR)[2]
+    return one, "port", "oracle/match_oracle.py (torch-CPU port of the reference op sequence incl. [O*P,HW] expansion)"
 
+
+def cpu_reference_rate(seconds_budget: float):
+    """The reference's CPU path on this host's cores, timed one problem at a time on a bounded sample."""
+    one, kind, what = reference_callable()
     threads = tune_cpu_threads(one)                                   # also warms up
     n, t0 = 0, time.perf_counter()
     while True:
@@ -148,26 +175,15 @@ def cpu_reference_rate(seconds_budget: float, threads: int):
         el = time.perf_counter() - t0
         if el >= seconds_budget or n >= 200:
             break
-    return n / el, n, el, threads
+    return n / el, n, el, threads, kind, what
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the python reference tree
-    does not exist on the GPU box), all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path, all the host threads it can use, rank 0 only."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
     per_step_budget = max(0.5, min(4.0, 60.0 / max(1, args.steps + args.warmup)))
-    from oracle import match_oracle as orc
-    from dmm_net_b200.synth import make_problem
-    torch.set_num_threads(threads)
-    pr = make_problem(P, O, H, W, D, config=2, index=0)
-
-    def one():
-        with torch.no_grad():
-            sim, _ = orc.cost_matrix(pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, SCORE_W, None, expand=True)
-            orc.relax_solve(-sim, MAX_ITER, PROJ_ITER, LR)
-
+    one, kind, what = reference_callable()
     threads = tune_cpu_threads(one)
     t0 = time.perf_counter(); one(); t_one = time.perf_counter() - t0
     per_step = max(1, int(per_step_budget / max(t_one, 1e-3)))
@@ -183,10 +199,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "matches/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "matches_per_step": per_step},
-            "cpu_baseline": {"value": val, "unit": "matches/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps}x{per_step} problems of the headline shape, oracle/match_oracle.py "
-                                       f"(torch-CPU port of the reference op sequence, {threads} threads)"},
+            "config": dict(CONFIG), "run": {"matches_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": "matches/s", "cores": threads, "kind": kind,
+                             "sample": f"{args.steps}x{per_step} problems of the headline shape, {what}, {threads} threads"},
             "e2e": {"value": val, "unit": "matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -339,9 +354,11 @@ def main():
             "metric": METRIC, "value": value, "unit": "matches/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "problems_per_step_per_gpu": B, "k1_launches_per_step": chunks_seen[-1] if chunks_seen else None, "parallelism": f"dp{world} (problems sharded, no collective)",
-                       "l2": f"inputs {B * MASK_BYTES_PER_MATCH / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
-                       "full_step_gbs_per_gpu": ALGO_BYTES_PER_MATCH * B / (ms_total / args.steps * 1e-3) / 1e9},
+            "config": dict(CONFIG),
+            "run": {"problems_per_step_per_gpu": B, "k1_launches_per_step": chunks_seen[-1] if chunks_seen else None,
+                    "parallelism": f"dp{world} (problems sharded, no collective)",
+                    "l2": f"inputs {B * MASK_BYTES_PER_MATCH / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
+                    "full_step_gbs_per_gpu": ALGO_BYTES_PER_MATCH * B / (ms_total / args.steps * 1e-3) / 1e9},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "matches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "problems_per_step": Be, "host_bytes_packed_per_step": e2e_info.get("packed"),
@@ -357,11 +374,9 @@ def main():
                          "algorithmic_bytes_per_launch": MASK_BYTES_PER_MATCH * B, "kernel_ms": k1_ms},
         }
         if world == 1 and args.cpu_seconds > 0:
-            threads = os.cpu_count() or 1
-            rate, n, el, threads = cpu_reference_rate(args.cpu_seconds, threads)
-            line["cpu_baseline"] = {"value": rate, "unit": "matches/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n} problems of the headline shape in {el:.1f} s, oracle/match_oracle.py "
-                                              f"(torch-CPU port of the reference op sequence incl. [O*P,HW] expansion)"}
+            rate, n, el, threads, kind, what = cpu_reference_rate(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": "matches/s", "cores": threads, "kind": kind,
+                                    "sample": f"{n} problems of the headline shape in {el:.1f} s, {what}"}
         prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(prof):
             try:

@@ -123,7 +123,8 @@ class DMM_Model(nn.Module):
         if torch.is_grad_enabled() and any(tplt_dict[b]['feat'][t].requires_grad for b in range(B) for t in range(T)):
             # training: every frame gets its own stack node in the autograd graph, like the reference's per-frame rebuild
             return torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)
-        key = tuple(id(tplt_dict[b]['feat'][t]) for b in range(B) for t in range(T))
+        # identity AND content version of every tensor: an in-place update (copy_, mul_, a momentum update) keeps id()
+        key = tuple((id(x), x.data_ptr(), x._version) for x in (tplt_dict[b]['feat'][t] for b in range(B) for t in range(T)))
         cached = getattr(self, '_tmpl_cache', None)
         if cached is None or cached[0] != key:
             stacked = torch.stack([torch.stack([tplt_dict[b]['feat'][t] for t in range(T)], 0) for b in range(B)], 0)

@@ -10,6 +10,7 @@ optional int32 ``n_prop[B]`` / ``n_tmpl[B]`` give the number of real rows per pr
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -17,6 +18,78 @@ import torch
 from . import _lib
 
 _VP = ctypes.c_void_p
+
+
+# ----------------------------------------------------------------------------------------------------------
+# device guard + optional per-op CUDA-event timing
+# ----------------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Collects (op name, start event, end event) for every public op while installed with ``set_kernel_timer``
+    (bench.py's clip legs report each op's share of the frame from it).  Events are recorded on the stream the op
+    launches on; nothing synchronises until ``totals()``."""
+
+    def __init__(self):
+        self.spans = []
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.spans:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+_TIMER: Optional[KernelTimer] = None
+_TIMER_DEPTH = 0
+
+
+def set_kernel_timer(timer: Optional[KernelTimer]) -> None:
+    global _TIMER
+    _TIMER = timer
+
+
+def _first_cuda_device(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, RaggedMasks):
+            return a.device
+        elif isinstance(a, (list, tuple)) and a and isinstance(a[0], torch.Tensor) and a[0].is_cuda:
+            return a[0].device
+    return None
+
+
+def _op(name: str):
+    """Every public op runs with the CUDA device of its tensors current (the C ABI launches on the current device's
+    stream: without the guard, tensors of a non-current device would be handed to kernels of another GPU), and is
+    timed when a KernelTimer is installed (outermost op only)."""
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrap(*args, **kwargs):
+            global _TIMER_DEPTH
+            dev = _first_cuda_device(args, kwargs)
+            if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    return wrap(*args, **kwargs)
+            t = _TIMER
+            if t is None or _TIMER_DEPTH > 0:
+                return fn(*args, **kwargs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            _TIMER_DEPTH += 1
+            try:
+                e0.record()
+                out = fn(*args, **kwargs)
+                e1.record()
+            finally:
+                _TIMER_DEPTH -= 1
+            t.spans.append((name, e0, e1))
+            return out
+
+        return wrap
+
+    return deco
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -41,6 +114,29 @@ def _counts(t: Optional[torch.Tensor], B: int, dev) -> Optional[torch.Tensor]:
     t = torch.as_tensor(t, device=dev).to(torch.int32).contiguous()
     assert t.shape == (B,), t.shape
     return t
+
+
+_LIMITS = None
+
+
+def limits() -> dict:
+    """Shape envelope of the solver kernel (dmm_b200_limits): the whole [O x max(P, O+1)] problem lives in the registers
+    of one CTA, so O (template slots = the reference's ``-maxseqlen``) and P (``sort_max_num``) are bounded."""
+    global _LIMITS
+    if _LIMITS is None:
+        out = (ctypes.c_int * 4)()
+        _lib.check(_lib.load().dmm_b200_limits(out), "dmm_b200_limits")
+        _LIMITS = {"max_templates": int(out[0]), "max_solver_cols": int(out[1]), "max_batch": int(out[2])}
+    return _LIMITS
+
+
+def check_solver_shape(P: int, O: int) -> None:
+    lim = limits()
+    if O > lim["max_templates"] or pad_cols(P, O) > lim["max_solver_cols"]:
+        raise RuntimeError(
+            f"dmm_net_b200: the relaxed-matching kernel holds one problem per CTA and supports at most "
+            f"{lim['max_templates']} template slots (-maxseqlen) and {lim['max_solver_cols']} proposals (sort_max_num); "
+            f"got O={O}, P={P}. Lower -maxseqlen / sort_max_num, or pass only the valid templates.")
 
 
 def pad_cols(P: int, O: int) -> int:
@@ -77,6 +173,7 @@ class RaggedMasks:
 # ----------------------------------------------------------------------------------------------------------
 # K1  mask IoU
 # ----------------------------------------------------------------------------------------------------------
+@_op("K1 mask_iou")
 def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[torch.Tensor] = None,
                       n_prop=None, n_tmpl=None, cos: Optional[torch.Tensor] = None, w_cos: float = 0.0,
                       w_iou: float = 0.0, want_counts: bool = False):
@@ -145,6 +242,7 @@ def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[to
     return out
 
 
+@_op("K1 mask_iou_rowwise")
 def mask_iou_rowwise(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a [N,M], b [N,M] -> iou [N]  (compute_iou_binary_mask_2D, match_helper.py:9-28)."""
     lib = _lib.load()
@@ -191,6 +289,7 @@ def pack_masks_host(masks: torch.Tensor, mask_dims: int = 2, threads: int = 0, o
     return out
 
 
+@_op("mask_pack_bits")
 def pack_masks(masks: torch.Tensor, mask_dims: int = 2) -> torch.Tensor:
     """DEVICE fp32 masks [..., H, W] -> DEVICE int32 bit planes [..., words]."""
     lib = _lib.load()
@@ -211,6 +310,7 @@ def pack_masks(masks: torch.Tensor, mask_dims: int = 2) -> torch.Tensor:
     return out
 
 
+@_op("K1 mask_iou_packed")
 def mask_iou_pairwise_packed(prop_bits: torch.Tensor, tmpl_bits: torch.Tensor, tmpl2_bits: Optional[torch.Tensor] = None,
                              n_prop=None, n_tmpl=None, cos: Optional[torch.Tensor] = None, w_cos: float = 0.0,
                              w_iou: float = 0.0, want_counts: bool = False):
@@ -293,6 +393,7 @@ class _CosineFn(torch.autograd.Function):
 COSINE_IMPLS = {"auto": 0, "simt": 1, "tc": 2}
 
 
+@_op("K2 cosine")
 def cosine_pairwise(tmpl_feat: torch.Tensor, prop_feat: torch.Tensor, n_prop=None, n_tmpl=None, eps: float = 1e-8,
                     impl: Optional[str] = None):
     """tmpl_feat [B,T,O,D] (T template-feature sets), prop_feat [B,P,D] -> mean_t cos [B,O,P]; differentiable.
@@ -359,12 +460,14 @@ class _SolveFn(torch.autograd.Function):
         return g_mat, g_score, None, None, None, None, None, None, None, None, None
 
 
+@_op("K3 relax_solve")
 def relax_solve(mat: torch.Tensor, score: Optional[torch.Tensor] = None, n_prop=None, n_tmpl=None,
                 max_iter: int = 20, proj_iter: int = 5, lr: float = 0.1, negate: bool = True, pad_rule: bool = True,
                 is_test: bool = True, want_xlist: bool = False):
     """mat [B,O,P] (similarity when negate else cost) -> (R, Bmat, match_score, det_score, X_final, logic, n_list[, xlist, cost])."""
     mat = _cuda_f32(mat, "mat")
     B = mat.shape[0]
+    check_solver_shape(mat.shape[2], mat.shape[1])
     if score is not None:
         score = _cuda_f32(score, "prop_score")
         assert score.shape == (B, mat.shape[2]), (score.shape, mat.shape)
@@ -446,6 +549,7 @@ class _ApplyRaggedFn(torch.autograd.Function):
         return gB, None, None, None, None, None, None, None
 
 
+@_op("K4 assign_apply")
 def assign_apply(Bm: torch.Tensor, prop: torch.Tensor, logic: Optional[torch.Tensor] = None, n_prop=None, n_tmpl=None,
                  row_map: Optional[torch.Tensor] = None, O_out: Optional[int] = None, zero_fill: bool = True):
     """Bmat [B,O,MS] x prop [B,P,HW] -> out [B,O_out,HW]; row o of problem b lands in row row_map[b,o].
@@ -517,6 +621,7 @@ class _RoiPoolFn(torch.autograd.Function):
         return (None, *gf)
 
 
+@_op("K5 roi_mean_pool")
 def roi_mean_pool(features: Sequence[torch.Tensor], rois: torch.Tensor) -> torch.Tensor:
     """4 levels [N,C,Hl,Wl] at strides 4/8/16/32, rois [R,5] = (batch idx, x1, y1, x2, y2) -> [R, 4*C]."""
     assert len(features) == 4, "FeatureExtractor pools 4 levels (feature_extractor.py:13)"
@@ -579,6 +684,7 @@ class _PyramidFn(torch.autograd.Function):
         return grads[0], grads[1], grads[2], None, None, None
 
 
+@_op("K6 mask_pyramid")
 def mask_pyramid(prev_mask: torch.Tensor, ref_mask: torch.Tensor, init_pred: torch.Tensor, n_levels: int = 4):
     """The decoder's mask inputs for EVERY object in one pass (trainer.py:256-263, evaluator.py:187-194).
 
@@ -593,6 +699,7 @@ def mask_pyramid(prev_mask: torch.Tensor, ref_mask: torch.Tensor, init_pred: tor
     return list(_PyramidFn.apply(prev, ref, init, int(H), int(W), int(n_levels)))
 
 
+@_op("K7 merge_labels")
 def merge_labels(outs: torch.Tensor, n_valid=None) -> torch.Tensor:
     """outs [B,O,HW] (or [B,O,H,W]) sigmoid masks -> uint8 label map [B,HW]: 0 = background, t+1 = object t
     (evaluator.py:139-145, for all videos of the batch at once; ``n_valid[b]`` = tplt_valid_batch[b].sum())."""
@@ -623,6 +730,7 @@ def hard_iou_mean(y_mask: torch.Tensor, pred: torch.Tensor, valid: torch.Tensor)
 # ----------------------------------------------------------------------------------------------------------
 # K8 / K9  rows before the layer: proposal paste (+ bit rows + tight boxes), box NMS
 # ----------------------------------------------------------------------------------------------------------
+@_op("K8 paste_masks")
 def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, im_h: int, im_w: int, thresh: float = 0.5, padding: int = 1,
                 want_pasted: bool = True, want_bits: bool = False, want_tight: bool = True):
     """masks [N,1,M,M] or [N,M,M] soft, boxes [N,4] xyxy -> dict(pasted [N,im_h,im_w], bits [N,words] int32, tight [N,4]
@@ -647,6 +755,7 @@ def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, im_h: int, im_w: int, 
     return out
 
 
+@_op("K10 paste_apply")
 def paste_apply(Bm: torch.Tensor, masks: torch.Tensor, boxes: torch.Tensor, src_index: torch.Tensor, im_h: int, im_w: int,
                 n_prop=None, n_tmpl=None, row_map: Optional[torch.Tensor] = None, O_out: Optional[int] = None,
                 zero_fill: bool = True, padding: int = 1) -> torch.Tensor:
@@ -681,6 +790,7 @@ def paste_apply(Bm: torch.Tensor, masks: torch.Tensor, boxes: torch.Tensor, src_
     return out
 
 
+@_op("K9 box_nms")
 def box_nms(boxes: torch.Tensor, scores: torch.Tensor, thresh: float, max_keep: int = 0, n_boxes=None):
     """boxes [F,n,4] (or [n,4]), scores [F,n] (or [n]) -> (keep [F,n] int64 kept indices in score order, -1 padded; n_keep
     [F] int32).  Greedy NMS with the legacy +1 widths, one CTA per frame (boxlist_ops.py:15-29)."""
@@ -714,6 +824,7 @@ def _side_streams(dev: torch.device):
     return _SIDE_STREAMS[key]
 
 
+@_op("cost_and_solve (K2+K1+K3)")
 def cost_and_solve(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, max_iter: int, proj_iter: int, lr: float,
                    score_weight: float, is_test: bool, n_prop=None, n_tmpl=None, chunks: Optional[int] = None,
                    k1_events: Optional[list] = None):
@@ -743,6 +854,7 @@ def cost_and_solve(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, ma
         HW *= int(dsz)
     dev = prop_mask.device
     MS = pad_cols(P, O)
+    check_solver_shape(P, O)
     n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
     w = float(score_weight)
     new = lambda *shape: torch.empty(*shape, device=dev)
@@ -939,9 +1051,19 @@ def _fold_route_measurement(key):
 
 
 
-def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, max_iter: int, proj_iter: int, lr: float,
-                     score_weight: float, is_test: bool, device="cuda", threads: Optional[int] = None, n_prop=None,
-                     n_tmpl=None, raw_fraction: Optional[float] = None):
+def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, device="cuda", **kw):
+    """``_match_batch_host`` with ``device`` made current for the whole call (streams, events, allocations and the
+    C-ABI launches all follow the current device)."""
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        return _match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, device=dev, **kw)
+
+
+def _match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, max_iter: int, proj_iter: int, lr: float,
+                      score_weight: float, is_test: bool, device="cuda", threads: Optional[int] = None, n_prop=None,
+                      n_tmpl=None, raw_fraction: Optional[float] = None):
     """cost-build + solve for a batch whose inputs live in HOST memory (CPU fp32 tensors, pinned or not).
 
     Two routes feed the device at the same time:
@@ -954,8 +1076,11 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     (also when the masks are not pinned: the copy would not be asynchronous).  Both routes produce the same integer
     counts, so ``iou`` / ``sim`` are bit-identical whichever route a problem takes.
     Device side: K2 cosine -> K1 (fp32 rows | packed rows, +finalize/mix) -> K3 solver+head.  Returns the dict of
-    ``cost_and_solve`` (device tensors).  The soft masks stay on the host: the assignment-apply (which needs <= O selected
-    rows per problem) is left to the caller / ``match_batch``."""
+    ``cost_and_solve`` (device tensors) plus ``inputs_consumed``: a CUDA event that completes when the LAST host->device
+    copy reading the caller's buffers has finished.  **Buffer-reuse contract:** the call returns while those copies may
+    still be in flight (that is what lets consecutive calls overlap); a producer that refills the same pinned buffers in
+    place must ``out["inputs_consumed"].synchronize()`` first.  The soft masks stay on the host: the assignment-apply
+    (which needs <= O selected rows per problem) is left to the caller / ``match_batch``."""
     import time
     lib = _lib.load()
     for t in (prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score):
@@ -1031,7 +1156,9 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     pf, tf, sc = to_dev(prop_feat.contiguous()), to_dev(tmpl_feat.contiguous()), to_dev(prop_score.contiguous())
     n_prop, n_tmpl = _counts(n_prop, B, dev), _counts(n_tmpl, B, dev)
     sl = lambda t, a, b: None if t is None else t[a:b]
-    with torch.no_grad():
+    consumed = torch.cuda.Event()
+    consumed.record(main)                                        # every H2D copy on main is queued (re-recorded below when
+    with torch.no_grad():                                        #   the raw route is in use)
         cos = cosine_pairwise(tf, pf, n_prop, n_tmpl)
         w = float(score_weight)
         parts = [None, None]
@@ -1042,6 +1169,8 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
             main.wait_event(ev_dma)
             pm_raw.record_stream(main)
             tm_raw.record_stream(main)
+            consumed = torch.cuda.Event()
+            consumed.record(main)                                # after the wait on the raw DMA and every copy queued on main
             parts[0] = mask_iou_pairwise(pm_raw, tm_raw, None, sl(n_prop, 0, nraw), sl(n_tmpl, 0, nraw), cos=cos[:nraw],
                                          w_cos=1 - w, w_iou=w)
         parts = [q for q in parts if q is not None]
@@ -1059,7 +1188,7 @@ def match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *, 
     h2d = 4 * (prop_feat.numel() + tmpl_feat.numel() + prop_score.numel()) + 4 * npk * (P + O) * words + \
         4 * nraw * (P + O) * HW
     return {"cos": cos, "iou": iou, "sim": sim, "R": R, "Bmat": Bm, "logic": logic, "X_final": Xf,
-            "match_score": ms, "det_score": ds, "n_list": n_list, "h2d_bytes": h2d,
+            "match_score": ms, "det_score": ds, "n_list": n_list, "h2d_bytes": h2d, "inputs_consumed": consumed,
             "host_packed_bytes": 4 * npk * (P + O) * HW, "host_threads": th, "raw_problems": nraw, "packed_problems": npk,
             "host_pack_seconds": t_host, "route_estimate": _HOST_SPLIT.get(key),
             "host_seconds": {"enqueue_raw_route": t_raw_enqueued, "pack": t_host, "whole_call": time.perf_counter() - t_call}}

@@ -9,9 +9,24 @@ class BoxList(object):
     def __init__(self, bbox, image_size=None, mode="xyxy"):
         bbox = torch.as_tensor(bbox, dtype=torch.float32)
         assert bbox.dim() == 2 and bbox.shape[-1] == 4, bbox.shape
-        assert mode == "xyxy"
+        assert mode in ("xyxy", "xywh"), mode
         self.bbox, self.size, self.mode = bbox, image_size, mode
         self.extra_fields = {}
+
+    def convert(self, mode):
+        """xyxy <-> xywh with the legacy +1 pixel convention of maskrcnn_benchmark's BoxList.convert (TO_REMOVE = 1)."""
+        assert mode in ("xyxy", "xywh"), mode
+        if mode == self.mode:
+            return self
+        x0, y0, a, b = self.bbox.unbind(-1)
+        if mode == "xyxy":                                       # from xywh
+            bbox = torch.stack([x0, y0, x0 + (a - 1).clamp(min=0), y0 + (b - 1).clamp(min=0)], -1)
+        else:                                                    # xyxy -> xywh
+            bbox = torch.stack([x0, y0, a - x0 + 1, b - y0 + 1], -1)
+        out = BoxList(bbox, self.size, mode)
+        for k, v in self.extra_fields.items():
+            out.add_field(k, v)
+        return out
 
     def add_field(self, name, data):
         self.extra_fields[name] = data

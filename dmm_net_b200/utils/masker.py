@@ -34,6 +34,12 @@ class Masker(object):
         assert len(boxes) == len(masks), "Masks and boxes should have the same length."
         for mask, box in zip(masks, boxes):
             assert mask.shape[0] == len(box), "Number of objects should be the same."
+        # reference masker.py:184 converts every BoxList to xyxy before pasting
+        boxes = [b.convert("xyxy") if hasattr(b, "convert") else b for b in boxes]
+        for b in boxes:
+            assert getattr(b, "mode", "xyxy") == "xyxy", "Masker pastes xyxy boxes (BoxList.convert('xyxy') is missing)"
+            assert b.size is not None and len(tuple(b.size)) == 2, \
+                "Masker needs the image size: BoxList(bbox, image_size=(im_w, im_h))"
         sizes = {tuple(b.size) for b in boxes}
         results, results_box, results_bits = [None] * len(boxes), [None] * len(boxes), [None] * len(boxes)
         for size in sizes:                                     # images of one batch share a size: one launch

@@ -335,18 +335,21 @@ def roi_mean_pool_separable(features: Sequence[torch.Tensor], rois: torch.Tensor
 # --------------------------------------------------------------------------------------
 def dmm_container_forward(cfg, is_test, prop_feats: List[torch.Tensor], prop_masks: List[torch.Tensor],
                           prop_scores: List[torch.Tensor], tmpl_feat: List[torch.Tensor], mask_last: torch.Tensor,
-                          valid: torch.Tensor, targets: Optional[torch.Tensor] = None, expand: bool = False):
+                          valid: torch.Tensor, targets: Optional[torch.Tensor] = None, expand: bool = False,
+                          extra_frame: Optional[Sequence[int]] = None):
     """Per-video loop of DMM_Model.forward / .inference.
 
     prop_*[b]: tensors of video b; tmpl_feat[b]: [F,D]; mask_last: [B,F,H,W]; valid: [B,F] 0/1 with
-    the O valid templates first (the reference takes rows :O, dmm_model.py:125).
+    O = valid.sum() templates: the reference takes rows :O of diag(valid) and of the masks (dmm_model.py:125,152-154),
+    whatever the positions of the ones.  ``extra_frame[b]`` (inference only, dmm_model.py:66) skips video b.
+    Pinned to the reference by tests/golden/container_*.npz (oracle/make_golden_container.py).
     Returns (output_mask [B,F,H,W], match_loss list, out_mask_last [B,F,H,W])."""
     B, Fm, H, W = mask_last.shape
     outs, lasts, losses = [], [], []
     for b in range(B):
         v = valid[b]
         O = int(v.sum().item())
-        if O == 0:
+        if O == 0 or (extra_frame is not None and extra_frame[b]):
             outs.append(mask_last.new_zeros(Fm, H, W))
             lasts.append(mask_last[b])
             if not is_test:

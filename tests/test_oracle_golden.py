@@ -98,3 +98,78 @@ def test_roi_pool_separable_equals_roialign():
     b = orc.roi_mean_pool_separable(feats, rois)
     assert a.shape == (6, 24)
     np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# goldens of oracle/make_golden_container.py: the reference's DMM_Model container, algo='hun', the headline size
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("container_"))
+def test_container_matches_reference(name):
+    """oracle.dmm_container_forward == the unmodified reference DMM_Model.forward / .inference (dmm_model.py:48-158),
+    given the same pooled features (the reference's own FeatureExtractor over the stand-in ROIAlign)."""
+    g = load_golden(name)
+    B, P, Fm, H, W, C, mi, pi, is_test = [int(v) for v in g["meta"]]
+    n_prop = [int(v) for v in g["n_prop"]]
+    cfg = default_cfg(mi, pi)
+    feats = [T(g[f"feat{l}"]) for l in range(4)]
+    rois = torch.cat([torch.cat([torch.full((n_prop[b], 1), float(b)), T(g[f"boxes{b}"])], 1) for b in range(B)], 0)
+    pooled = orc.roi_mean_pool(feats, rois)
+    np.testing.assert_array_equal(pooled.numpy(), g["prop_pooled"])          # same stand-in ROIAlign arithmetic
+    trois = torch.cat([torch.cat([torch.full((Fm, 1), float(b)), T(g[f"tboxes{b}"])], 1) for b in range(B)], 0)
+    tpooled = orc.roi_mean_pool([T(g[f"tfeat{l}"]) for l in range(4)], trois).view(B, Fm, -1)
+    np.testing.assert_array_equal(tpooled.numpy(), g["tmpl_pooled"])
+    pm, sc = T(g["prop_mask"]), T(g["prop_score"])
+    out, loss, last = orc.dmm_container_forward(
+        cfg, is_test, list(pooled.split(n_prop, 0)), [pm[b, :n_prop[b]] for b in range(B)],
+        [sc[b, :n_prop[b]] for b in range(B)], list(tpooled.unbind(0)), T(g["tmpl_mask"]), T(g["valid"]),
+        None if is_test else T(g["targets"]), expand=True, extra_frame=[int(v) for v in g["extra_frame"]])
+    np.testing.assert_array_equal(out.numpy(), g["output_mask"])
+    np.testing.assert_array_equal(last.numpy(), g["out_mask_last"])
+    if not is_test:
+        np.testing.assert_array_equal(np.array([float(x) for x in loss], np.float32), g["match_loss"])
+
+
+@pytest.mark.parametrize("name", golden_names("hun_"))
+def test_hungarian_layer_matches_reference(name):
+    """algo='hun' (relax_match.py:120-126 + the head of match_model.py:125-147)."""
+    g = load_golden(name)
+    P, O, H, W, D, is_test = [int(v) for v in g["meta"]]
+    cfg = default_cfg(20, 5, algo="hun")
+    full, ms, ds, _, _ = orc.match_layer_forward(cfg, is_test, T(g["prop_feat"]), T(g["prop_mask"]), [T(g["tmpl_feat"])],
+                                                 T(g["tmpl_mask"]), T(g["prop_score"]))
+    np.testing.assert_array_equal(full.numpy(), g["full_outmask"])
+    np.testing.assert_array_equal(ms.numpy(), g["match_score"])
+    np.testing.assert_array_equal(ds.numpy(), g["det_score"])
+
+
+def big_inputs(g):
+    """Regenerates the headline-size inputs of a big_* golden and proves they are the bytes the reference saw."""
+    import hashlib
+    from dmm_net_b200.synth import make_problem
+    P, O, H, W, D, mi, pi, is_test, config, index, lattice = [int(v) for v in g["meta"]]
+    pr = make_problem(P, O, H, W, D, config=config, index=index)
+    h = hashlib.sha256()
+    for t in (pr.prop_feat, pr.prop_mask, pr.tmpl_feat, pr.tmpl_mask, pr.prop_score):
+        h.update(np.ascontiguousarray(t.numpy()).tobytes())
+    assert h.hexdigest() == str(g["input_sha"]), "seeded generator no longer reproduces the golden's inputs"
+    return pr, default_cfg(mi, pi), lattice
+
+
+@pytest.mark.parametrize("name", golden_names("big_"))
+def test_headline_size_layer_matches_reference(name):
+    """50 x 10 x 256x448 (and 255x448): the oracle against the reference's outputs at the size the bench runs."""
+    g = load_golden(name)
+    pr, cfg, lattice = big_inputs(g)
+    torch.set_num_threads(8)
+    try:
+        sim, _ = orc.cost_matrix(pr.prop_feat, pr.prop_mask, [pr.tmpl_feat], pr.tmpl_mask, cfg["score_weight"], None, expand=False)
+        full, ms, ds, logic, bmat, R = orc.assign_and_apply(sim, pr.prop_mask, pr.prop_score, cfg["relax_max_iter"],
+                                                            cfg["relax_proj_iter"], cfg["relax_learning_rate"], 1)
+    finally:
+        torch.set_num_threads(1)
+    np.testing.assert_allclose(sim.numpy(), g["sim"], rtol=0, atol=1e-6)      # multi-threaded sums: not bit-pinned
+    np.testing.assert_array_equal(logic.numpy(), g["logic"])
+    np.testing.assert_allclose(bmat.numpy(), g["bmat"], rtol=0, atol=1e-5)
+    flat = full.reshape(full.shape[0], -1)
+    np.testing.assert_allclose(flat[:, ::lattice].numpy(), g["full_lattice"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(flat.double().sum(1).numpy(), g["full_rowsum"], rtol=1e-6)
