@@ -29,6 +29,7 @@ SIGNATURES = {
     "dmm_packed_words": (_ll, [_ll]),
     "dmm_host_pack_masks": (_i, [_vp, _ll, _ll, _vp, _i]),
     "dmm_host_pack_masks2": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _i]),
+    "dmm_host_read_bandwidth": (_i, [_vp, _ll, _i, _i, POINTER(ctypes.c_double)]),
     "dmm_mask_pack_bits": (_i, [_vp, _ll, _i, _vp, _vp]),
     "dmm_mask_iou_packed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "dmm_mask_iou_pairwise_packed": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f,
@@ -49,7 +50,8 @@ SIGNATURES = {
     "dmm_assign_apply_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "dmm_assign_apply_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                   _vp]),
-    "dmm_roi_mean_pool": (_i, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, _vp, _vp]),
+    "dmm_roi_mean_pool_workspace_bytes": (_sz, [POINTER(c_int), POINTER(c_int), _i, _i, _i]),
+    "dmm_roi_mean_pool": (_i, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, _vp, _vp, _sz, _i, _vp]),
     "dmm_roi_mean_pool_bwd": (_i, [_vp, POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, POINTER(c_void_p), _vp]),
     "dmm_mask_pyramid_level_size": (_i, [_i, _i, _i, POINTER(c_int), POINTER(c_int)]),
     "dmm_mask_pyramid": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, POINTER(c_void_p), _vp]),
@@ -78,7 +80,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export what the header declares
         fn.restype = res
         fn.argtypes = args
-    if lib.dmm_b200_version() != 0x000100:
+    if lib.dmm_b200_version() != 0x000200:
         raise RuntimeError("libdmm_b200.so version mismatch: rebuild with `python -m dmm_net_b200.build --force`")
     _lib = lib
     return lib

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdmm_b200.so")
-SOURCES = ["abi.cu", "mask_iou.cu", "cosine.cu", "cosine_tc.cu", "relax_solve.cu", "assign_apply.cu", "roi_mean_pool.cu", "refine_inputs.cu", "proposal_paste.cu",
+SOURCES = ["abi.cu", "mask_iou.cu", "cosine.cu", "cosine_tc.cu", "relax_solve.cu", "assign_apply.cu", "roi_mean_pool.cu", "roi_pool_tc.cu", "refine_inputs.cu", "proposal_paste.cu",
            "host_pack.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-v"]

@@ -8,8 +8,12 @@
 #include <stddef.h>
 
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
+#include <vector>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -67,6 +71,63 @@ extern "C" long long dmm_packed_words(long long HW) { return (HW + 31) / 32; }
 
 namespace {
 
+// Persistent worker team: threads are created on first use, PARK on a condition variable between calls (no spinning: see
+// pack_jobs) and live until the process exits.  run(n, fn) executes fn on n threads (the caller is one of them) and
+// returns when all have finished.  One call at a time per process (a mutex serialises concurrent callers).
+class Team {
+ public:
+  void run(int n, const std::function<void()>& fn) {
+    std::lock_guard<std::mutex> call(call_mu_);
+    if (n <= 1) { fn(); return; }
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      while ((int)workers_.size() < n - 1) workers_.emplace_back([this, id = (int)workers_.size()] { loop(id); });
+      fn_ = &fn; want_ = n - 1; pending_ = n - 1; ++gen_;
+    }
+    cv_.notify_all();
+    fn();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+  ~Team() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) if (t.joinable()) t.join();
+  }
+
+ private:
+  void loop(int id) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void()>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        if (id >= want_) continue;                           // this call uses fewer threads
+        fn = fn_;
+      }
+      (*fn)();
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  const std::function<void()>* fn_ = nullptr;
+  unsigned long long gen_ = 0;
+  int want_ = 0, pending_ = 0;
+  bool stop_ = false;
+};
+
+Team& team() {
+  static Team t;
+  return t;
+}
+
 struct PackJob { const float* src; long long rows; uint32_t* dst; };
 
 int pack_jobs(const PackJob* jobs, int njobs, long long HW, int threads) {
@@ -84,9 +145,11 @@ int pack_jobs(const PackJob* jobs, int njobs, long long HW, int threads) {
   for (int j = 0; j < njobs; ++j) first[j + 1] = first[j] + jobs[j].rows * pieces;
   const long long tasks = first[njobs];
   if (tasks == 0) return DMM_OK;
-  // Plain std::threads per call, work claimed in blocks from an atomic counter.  (Round 1 used an OpenMP team: its idle
-  // workers SPIN after the parallel region, which under a cgroup CPU quota -- the GPU boxes give 128 logical CPUs a
-  // 16-CPU quota -- burns the quota and gets the whole process, kernel-launching thread included, throttled.)
+  // A parked team (Team below) runs the blocks; work is claimed from an atomic counter.  History: round 1 used an OpenMP
+  // team, whose idle workers SPIN after the parallel region -- under the GPU boxes' cgroup CPU quota (128 logical CPUs,
+  // 16-CPU quota) that burned the quota and got the whole process throttled; then plain std::threads created per call
+  // (tree start-up), which put 16 thread creations into every ~10 ms step.  Now the workers are created once and sleep
+  // on a condition variable between calls.
   long long nt = threads > 0 ? threads : (long long)std::thread::hardware_concurrency();
   const long long block = 8;           // tasks per claim: 1 MB of fp32
   if (nt > (tasks + block - 1) / block) nt = (tasks + block - 1) / block;
@@ -114,17 +177,7 @@ int pack_jobs(const PackJob* jobs, int njobs, long long HW, int threads) {
       }
     }
   };
-  // The team starts as a binary tree (thread i starts 2i+1 and 2i+2 before it works): the last of 16 threads is running
-  // after 4 thread creations instead of 15, which matters when the whole call is ~10 ms.
-  std::function<void(long long)> run = [&](long long id) {
-    std::thread c1, c2;
-    if (2 * id + 1 < nt) c1 = std::thread(run, 2 * id + 1);
-    if (2 * id + 2 < nt) c2 = std::thread(run, 2 * id + 2);
-    work();
-    if (c1.joinable()) c1.join();
-    if (c2.joinable()) c2.join();
-  };
-  run(0);
+  team().run((int)nt, work);
   return DMM_OK;
 }
 
@@ -145,4 +198,43 @@ extern "C" int dmm_host_pack_masks2(const float* src_a, long long rows_a, uint32
   if ((rows_a > 0 && (!src_a || !dst_a)) || (rows_b > 0 && (!src_b || !dst_b))) return DMM_ERR_INVALID_ARGUMENT;
   const PackJob jobs[2] = {{src_a, rows_a, dst_a}, {src_b, rows_b, dst_b}};
   return pack_jobs(jobs, 2, HW, threads);
+}
+
+// Streaming-read bandwidth of a host buffer with the packer's thread team (bench.py: the host-DRAM roofline of the
+// host-buffer entry -- every mask byte has to be read from host memory once, whichever route carries it).  Each thread
+// sums 64-byte lines of its blocks; returns GB/s of the best of `reps` passes through *gbs.
+extern "C" int dmm_host_read_bandwidth(const void* src, long long bytes, int threads, int reps, double* gbs) {
+  if (!src || !gbs || bytes <= 0 || reps <= 0) return DMM_ERR_INVALID_ARGUMENT;
+  const long long block = 1 << 20, nblocks = (bytes + block - 1) / block;
+  long long nt = threads > 0 ? threads : (long long)std::thread::hardware_concurrency();
+  if (nt > nblocks) nt = nblocks;
+  double best = 0.0;
+  std::atomic<unsigned long long> sink(0);
+  for (int r = 0; r < reps; ++r) {
+    std::atomic<long long> next(0);
+    auto work = [&]() {
+      unsigned long long acc = 0;
+      for (;;) {
+        const long long b = next.fetch_add(1, std::memory_order_relaxed);
+        if (b >= nblocks) break;
+        const long long lo = b * block, hi = lo + block < bytes ? lo + block : bytes;
+        const unsigned long long* q = (const unsigned long long*)((const char*)src + lo);
+        const long long n = (hi - lo) / 8;
+        unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        long long i = 0;
+        for (; i + 32 <= n; i += 32) {                       // 4 cache lines per iteration, every word touched
+          for (int k = 0; k < 8; ++k) { a0 += q[i + k]; a1 += q[i + 8 + k]; a2 += q[i + 16 + k]; a3 += q[i + 24 + k]; }
+        }
+        for (; i < n; ++i) a0 += q[i];
+        acc += a0 + a1 + a2 + a3;
+      }
+      sink.fetch_add(acc, std::memory_order_relaxed);
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    team().run((int)nt, work);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (sec > 0 && bytes / sec / 1e9 > best) best = bytes / sec / 1e9;
+  }
+  *gbs = best + (sink.load() == 0xdeadbeefULL ? 1e-30 : 0.0);   // keep the sums alive
+  return DMM_OK;
 }

@@ -25,6 +25,7 @@ struct PoolParams {
   float* gfeat[4];
   int H[4], W[4];
   int N, C, R;
+  int level_skip;      // bit l set: level l is computed elsewhere (tensor-core path), this kernel leaves it alone
   const float* rois;   // [R][5]
   float* out;          // [R][4*C]
   const float* gout;
@@ -68,6 +69,7 @@ template <bool BWD, bool TABLE>
 __global__ void __launch_bounds__(kThreads) roi_mean_pool_kernel(const PoolParams p) {
   extern __shared__ float wsm[];  // wy[H] wx[W] | table: off[hh*ww] (int), w[hh*ww] (float)
   const int r = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((p.level_skip >> l) & 1) return;
   const int H = p.H[l], W = p.W[l];
   const float scale = 0.25f / (float)(1 << l);  // 1/4, 1/8, 1/16, 1/32 (feature_extractor.py:13)
   const float* roi = p.rois + (long long)r * 5;
@@ -185,20 +187,44 @@ static int fill(PoolParams& kp, const int Hl[4], const int Wl[4], int N, int C, 
     if (need > tab) tab = need;
   }
   table_smem = tab <= 200 * 1024 ? tab : 0;   // backward; 0: feature maps too large for the window table -> index math path
-  kp.N = N; kp.C = C; kp.R = R; kp.rois = rois; kp.out = nullptr; kp.gout = nullptr;
+  kp.N = N; kp.C = C; kp.R = R; kp.rois = rois; kp.out = nullptr; kp.gout = nullptr; kp.level_skip = 0;
   return DMM_OK;
 }
 
+namespace dmm {
+size_t roi_pool_tc_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R);
+int roi_pool_tc_try_launch(const float* const feat[4], const int Hl[4], const int Wl[4], int N, int C, const float* rois, int R,
+                           float* out, void* workspace, size_t workspace_bytes, int* level_mask, cudaStream_t st);
+}  // namespace dmm
+
+extern "C" size_t dmm_roi_mean_pool_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R) {
+  if (!Hl || !Wl) return 0;
+  return roi_pool_tc_workspace_bytes(Hl, Wl, N, C, R);
+}
+
+// impl: 0 = auto (tensor-core path for every level inside its envelope when a workspace is given, SIMT kernel for the
+// rest), 1 = SIMT kernel only, 2 = tensor-core path required for at least one level (DMM_ERR_UNSUPPORTED_SHAPE otherwise).
 extern "C" int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], const int Wl[4], int N, int C,
-                                 const float* rois, int R, float* out, void* stream) {
+                                 const float* rois, int R, float* out, void* workspace, size_t workspace_bytes, int impl,
+                                 void* stream) {
   PoolParams kp; size_t smem, tsmem;
   int rc = fill(kp, Hl, Wl, N, C, rois, R, smem, tsmem);
   if (rc) return rc;
+  if (impl < 0 || impl > 2) return DMM_ERR_INVALID_ARGUMENT;
   if (R == 0 || C == 0) return DMM_OK;
   if (!feat || !rois || !out) return DMM_ERR_INVALID_ARGUMENT;
   for (int l = 0; l < 4; ++l) { if (!feat[l]) return DMM_ERR_INVALID_ARGUMENT; kp.feat[l] = feat[l]; }
   kp.out = out;
   (void)tsmem;
+  int tc_mask = 0;
+  if (impl != 1) {
+    rc = roi_pool_tc_try_launch(feat, Hl, Wl, N, C, rois, R, out, workspace, workspace_bytes, &tc_mask, (cudaStream_t)stream);
+    if (rc > 0) return rc;
+    if (rc < 0) tc_mask = 0;
+    if (impl == 2 && tc_mask == 0) return DMM_ERR_UNSUPPORTED_SHAPE;
+  }
+  if (tc_mask == 15) return DMM_OK;
+  kp.level_skip = tc_mask;
   const size_t fsmem = smem + (size_t)kTabCap * 8;            // wy, wx + one table chunk: ~17 KB, 8 CTAs per SM
   if (fsmem > 48 * 1024)
     DMM_CUDA_TRY(cudaFuncSetAttribute(roi_mean_pool_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));

@@ -588,7 +588,7 @@ def assign_apply(Bm: torch.Tensor, prop: torch.Tensor, logic: Optional[torch.Ten
 # ----------------------------------------------------------------------------------------------------------
 class _RoiPoolFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rois, *feats):
+    def forward(ctx, rois, impl, *feats):
         lib = _lib.load()
         N, C = feats[0].shape[:2]
         R = rois.shape[0]
@@ -597,7 +597,10 @@ class _RoiPoolFn(torch.autograd.Function):
         Wl = (ctypes.c_int * 4)(*[f.shape[3] for f in feats])
         ptrs = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in feats])
         if R * C > 0:
-            rc = lib.dmm_roi_mean_pool(ptrs, Hl, Wl, N, C, _p(rois), R, _p(out), _stream())
+            ws_bytes = 0 if impl == "simt" else lib.dmm_roi_mean_pool_workspace_bytes(Hl, Wl, N, C, R)
+            ws = torch.empty(ws_bytes, device=rois.device, dtype=torch.uint8) if ws_bytes else None
+            rc = lib.dmm_roi_mean_pool(ptrs, Hl, Wl, N, C, _p(rois), R, _p(out), _p(ws), ws_bytes, ROI_POOL_IMPLS[impl],
+                                       _stream())
             _lib.check(rc, "dmm_roi_mean_pool")
         ctx.save_for_backward(rois)
         ctx.shapes = [tuple(f.shape) for f in feats]
@@ -618,12 +621,17 @@ class _RoiPoolFn(torch.autograd.Function):
         if R * C > 0:
             rc = lib.dmm_roi_mean_pool_bwd(_p(g_out), Hl, Wl, N, C, _p(rois), R, ptrs, _stream())
             _lib.check(rc, "dmm_roi_mean_pool_bwd")
-        return (None, *gf)
+        return (None, None, *gf)
+
+
+ROI_POOL_IMPLS = {"auto": 0, "simt": 1, "tc": 2}
 
 
 @_op("K5 roi_mean_pool")
-def roi_mean_pool(features: Sequence[torch.Tensor], rois: torch.Tensor) -> torch.Tensor:
-    """4 levels [N,C,Hl,Wl] at strides 4/8/16/32, rois [R,5] = (batch idx, x1, y1, x2, y2) -> [R, 4*C]."""
+def roi_mean_pool(features: Sequence[torch.Tensor], rois: torch.Tensor, impl: str = "auto") -> torch.Tensor:
+    """4 levels [N,C,Hl,Wl] at strides 4/8/16/32, rois [R,5] = (batch idx, x1, y1, x2, y2) -> [R, 4*C].
+    ``impl``: "auto" (tensor-core contraction per frame where the shapes allow -- C == 128, Wl % 4 == 0 or a tiny level --
+    and the SIMT gather kernel for the rest), "simt", "tc" (raise if no level can take the tensor-core path)."""
     assert len(features) == 4, "FeatureExtractor pools 4 levels (feature_extractor.py:13)"
     feats = [_cuda_f32(f, "feature") for f in features]
     N, C = feats[0].shape[:2]
@@ -631,7 +639,7 @@ def roi_mean_pool(features: Sequence[torch.Tensor], rois: torch.Tensor) -> torch
         assert f.dim() == 4 and f.shape[0] == N and f.shape[1] == C, [tuple(g.shape) for g in feats]
     rois = _cuda_f32(rois, "rois")
     assert rois.dim() == 2 and rois.shape[1] == 5, rois.shape
-    return _RoiPoolFn.apply(rois, *feats)
+    return _RoiPoolFn.apply(rois, impl, *feats)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -29,32 +29,13 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from backbone import Encoder                                        # noqa: E402
 from dmm_net_b200 import ops                                         # noqa: E402
 from dmm_net_b200.modules.dmm_model import DMM_Model                # noqa: E402
 from dmm_net_b200.synth import default_cfg                          # noqa: E402
 from dmm_net_b200.utils.boxlist import BoxList                      # noqa: E402
 from dmm_net_b200.utils.masker import Masker                        # noqa: E402
-
-
-class Encoder(nn.Module):
-    """ResNet-50 trunk + 1x1 neck convs to 128 channels per level (base.py:35-54)."""
-
-    def __init__(self, arch="resnet50"):
-        super().__init__()
-        import torchvision
-        net = getattr(torchvision.models, arch)(weights=None)
-        self.stem = nn.Sequential(net.conv1, net.bn1, net.relu, net.maxpool)
-        self.layers = nn.ModuleList([net.layer1, net.layer2, net.layer3, net.layer4])
-        chans = [256, 512, 1024, 2048] if arch != "resnet18" else [64, 128, 256, 512]
-        self.neck = nn.ModuleList([nn.Conv2d(c, 128, 1) for c in chans])
-
-    def forward(self, x):
-        x = self.stem(x)
-        outs = []
-        for layer, neck in zip(self.layers, self.neck):
-            x = layer(x)
-            outs.append(neck(x))
-        return tuple(outs)                                           # strides 4, 8, 16, 32
 
 
 class TinyDecoder(nn.Module):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMM_B200_VERSION 0x000100 /* 0.1.0 */
+#define DMM_B200_VERSION 0x000200 /* 0.2.0 */
 
 enum {
   DMM_OK = 0,
@@ -83,6 +83,9 @@ int dmm_host_pack_masks(const float* src_host, long long rows, long long HW, uin
 /* two row sets of the same HW (a problem's proposal and template masks) packed by ONE thread team */
 int dmm_host_pack_masks2(const float* src_a, long long rows_a, uint32_t* dst_a, const float* src_b, long long rows_b,
                          uint32_t* dst_b, long long HW, int threads);
+/* Streaming-read bandwidth (GB/s, best of `reps` passes) of a host buffer with the packer's parked thread team: the
+ * host-DRAM roofline of the host-buffer entry (bench.py e2e.host_dram_read_gbs). */
+int dmm_host_read_bandwidth(const void* src, long long bytes, int threads, int reps, double* gbs);
 int dmm_mask_pack_bits(const float* masks, long long rows, int HW, uint32_t* bits, void* stream);
 size_t dmm_mask_iou_packed_workspace_bytes(int B, int P, int O, int words, int two_template_sets);
 int dmm_mask_iou_pairwise_packed(const uint32_t* prop_bits, long long prop_bstride_words, const uint32_t* tmpl_bits,
@@ -179,9 +182,17 @@ int dmm_assign_apply_bwd_ptrs(const float* g_out, long long gout_bstride, const 
  * scales 1/4..1/32) on each of 4 levels followed by the spatial mean, i.e. the separable contraction
  *   out[r, l*C + c] = sum_y sum_x wy[r,l,y] * wx[r,l,x] * F_l[b_r, c, y, x].
  * feat[l] is [N][C][Hl][Wl]; rois [R][5] = (batch index, x1, y1, x2, y2) in image pixels; out [R][4*C].
+ *
+ * Two implementations behind one entry: the tensor-core path (csrc/roi_pool_tc.cu: per frame, the ROIs are the N
+ * dimension of a tcgen05 GEMM over TMA-streamed feature rows, so every feature byte is read once per frame) for C == 128
+ * and every level with Wl % 4 == 0 (or Hl*Wl <= 128), and the SIMT gather kernel for anything else.  `workspace`
+ * (dmm_roi_mean_pool_workspace_bytes, 256-byte aligned; may be NULL -> SIMT only) holds the ROI buckets, weight tables
+ * and band partials.  impl: 0 auto, 1 SIMT only, 2 tensor-core path required (DMM_ERR_UNSUPPORTED_SHAPE otherwise).
  */
+size_t dmm_roi_mean_pool_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R);
 int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], const int Wl[4], int N, int C,
-                      const float* rois, int R, float* out, void* stream);
+                      const float* rois, int R, float* out, void* workspace, size_t workspace_bytes, int impl,
+                      void* stream);
 /* g_feat[l] [N][C][Hl][Wl] must be zero-initialised by the caller; gradients are accumulated with atomics. */
 int dmm_roi_mean_pool_bwd(const float* g_out, const int Hl[4], const int Wl[4], int N, int C, const float* rois,
                           int R, float* const g_feat[4], void* stream);

@@ -42,7 +42,7 @@ def test_header_arity_matches_ctypes_table():
 
 def test_queries_work_without_a_device():
     lib = _lib.load()
-    assert lib.dmm_b200_version() == 0x000100
+    assert lib.dmm_b200_version() == 0x000200
     assert lib.dmm_b200_arch() == b"sm_100a"
     assert lib.dmm_b200_error_string(0) == b"ok" and b"workspace" in lib.dmm_b200_error_string(3)
     lim = (ctypes.c_int * 4)()

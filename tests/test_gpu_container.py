@@ -48,6 +48,61 @@ def test_roi_mean_pool_forward_and_backward():
         np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-4, atol=1e-5)   # fp32 atomics order
 
 
+def _tc_case(gen, N, H, W, counts, C=128):
+    """feature levels + a ROI table with `counts[n]` boxes for frame n, rows shuffled, plus edge-case boxes"""
+    feats = _feats(gen, N, C, H, W)
+    rows = [torch.cat([torch.full((c, 1), float(n)), _boxes(gen, c, H, W)], 1) for n, c in enumerate(counts) if c > 0]
+    rois = torch.cat(rows, 0)
+    edge = torch.tensor([[0, -30.0, -10.0, 20.0, 40.0], [N - 1, W - 8.0, H - 6.0, W + 22.0, H + 24.0],   # sticking out
+                         [0, 100.0, 100.0, 100.0, 100.0], [0, 0.0, 0.0, W - 1.0, H - 1.0],              # point, whole image
+                         [N - 1, -500.0, -500.0, -400.0, -400.0], [0, 3.3, 4.4, 9.9, 8.8],              # fully outside, tiny
+                         [-1, 10.0, 10.0, 50.0, 50.0], [N, 10.0, 10.0, 50.0, 50.0]])                   # frames that do not exist
+    rois = torch.cat([rois, edge], 0)
+    return feats, rois[torch.randperm(rois.shape[0], generator=gen)]
+
+
+@pytest.mark.parametrize("N,H,W,counts", [
+    (3, 256, 448, [50, 0, 9]),             # 64x112 / 32x56 / 16x28 rows on the tensor cores, the 8x14 level in linear mode
+    (2, 255, 448, [130, 70]),              # the scripts' 255x448; 3 + 2 groups of <= 64 ROIs per frame
+    (2, 128, 192, [20, 5]),                # level 3 is 4x6: linear mode
+    (1, 160, 224, [33]),                   # 10x14 and 5x7 cannot go through TMA: those two levels use the gather kernel
+    (1, 64, 1024, [12]),                   # 256-wide level 0: two 128-element x segments
+    (9, 64, 96, [7] * 9),
+])
+def test_roi_mean_pool_tensor_core_path(N, H, W, counts):
+    """K5-TC (csrc/roi_pool_tc.cu) against the ROIAlign stand-in oracle and against the gather kernel; frames with
+    several ROI groups, empty frames, shuffled rows, boxes sticking out of / outside the image, invalid frame ids."""
+    gen = torch.Generator().manual_seed(100 + N + H)
+    feats, rois = _tc_case(gen, N, H, W, counts)
+    dfeats, drois = [f.to(DEV) for f in feats], rois.to(DEV)
+    got = ops.roi_mean_pool(dfeats, drois, impl="tc")
+    simt = ops.roi_mean_pool(dfeats, drois, impl="simt")
+    ok = (rois[:, 0] >= 0) & (rois[:, 0] < N)
+    want = torch.zeros(rois.shape[0], 512)
+    want[ok] = orc.roi_mean_pool(feats, rois[ok])
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(got.cpu().numpy(), simt.cpu().numpy(), rtol=0, atol=5e-6)
+    assert float(got[~ok.to(DEV)].abs().sum()) == 0.0
+    assert torch.equal(got, ops.roi_mean_pool(dfeats, drois, impl="auto"))            # auto == tc inside the envelope
+    # the same box pools to the same bits whatever table it arrives in (row order, neighbours, table size)
+    sub = torch.cat([drois[5:12], drois[:3]], 0)
+    assert torch.equal(ops.roi_mean_pool(dfeats, sub, impl="tc"), torch.cat([got[5:12], got[:3]], 0))
+    assert torch.equal(got, ops.roi_mean_pool(dfeats, drois, impl="tc"))              # run to run
+
+
+def test_roi_mean_pool_tensor_core_envelope():
+    gen = torch.Generator().manual_seed(5)
+    feats = [f.to(DEV) for f in _feats(gen, 1, 128, 168, 216)]                          # 42x54, 21x27, 10x13, 5x6: no level fits
+    rois = torch.tensor([[0, 10.0, 10.0, 90.0, 120.0]], device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.roi_mean_pool(feats, rois, impl="tc")
+    a = ops.roi_mean_pool(feats, rois, impl="auto")
+    assert torch.equal(a, ops.roi_mean_pool(feats, rois, impl="simt"))
+    feats24 = [f.to(DEV) for f in _feats(gen, 1, 24, 256, 448)]                         # C != 128 -> gather kernel
+    with pytest.raises(RuntimeError):
+        ops.roi_mean_pool(feats24, rois, impl="tc")
+
+
 def test_feature_extractor_module_layout():
     gen = torch.Generator().manual_seed(8)
     feats = [f.to(DEV) for f in _feats(gen, 2, 128, 128, 192)]
