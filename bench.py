@@ -206,6 +206,116 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _load_example(name):
+    import importlib.util
+    ex = os.path.join(ROOT, "examples")
+    if ex not in sys.path:
+        sys.path.insert(0, ex)
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ex, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _shares(op_ms):
+    tot = sum(op_ms.values()) or 1.0
+    return {k: {"ms": round(v, 3), "share": round(v / tot, 4)} for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1])}
+
+
+def leg_clip_r50(dev, local_rank):
+    """BASELINE configs[2]: ResNet-50 backbone (stock torch) + K5 pooled features -> cosine cost + mask IoU -> solver ->
+    apply, on 8-frame clips, N=50 proposals, K=10 templates, 256x448, one GPU.  8 clips advance together (one batch per
+    frame); the frames of a clip are sequential."""
+    ce = _load_example("synthetic_clip_eval")
+    clips, frames = 8, 8
+    with ClockSampler(local_rank) as clk:
+        ce.clip_eval(clips, 3, 50, 10, (H, W), lazy=False, arch="resnet50", fixed_objects=True)          # warm-up (cuDNN autotune, allocator)
+        torch.cuda.synchronize()
+        clk.mark("start")
+        r = ce.clip_eval(clips, frames + 1, 50, 10, (H, W), lazy=False, arch="resnet50", fixed_objects=True, time_ops=True)
+        rl = ce.clip_eval(clips, frames + 1, 50, 10, (H, W), lazy=True, arch="resnet50", fixed_objects=True)
+        clk.mark("end")
+    return {"workload": "configs[2]: ResNet-50 + neck (stock torch) -> K8 paste -> K9 NMS -> K5 pooling -> K2 cosine + K1 IoU -> K3 -> K4 "
+                        "-> K6 pyramid + K7 labels; 8 clips x 8 frames, N=50 K=10 256x448, eval.yaml 40x5, 1 GPU",
+            "frames_per_s": r["frames"] / (r["ms"] * 1e-3), "ms_per_frame_step": r["ms_per_frame_step"], "clips_in_flight": clips,
+            "lazy_pipeline_frames_per_s": rl["frames"] / (rl["ms"] * 1e-3),
+            "per_op": _shares(r["op_ms"]), "clocks": clk.summary()}
+
+
+def leg_eval_r101(dev, local_rank, rank, world):
+    """BASELINE configs[3]: ResNet-101, YouTube-VOS-shaped synthetic clips (27 frames, 1..5 objects of F=5, N=50, 255x448),
+    clips sharded clip % world == rank, DMM_Model.inference_lazy; no collective in the data path."""
+    from dmm_net_b200.sharding import max_over_ranks, shard_indices, sum_over_ranks
+    ce = _load_example("synthetic_clip_eval")
+    clips_total, frames = 8 * world, 27
+    mine = shard_indices(clips_total, rank, world)
+    with ClockSampler(local_rank) as clk:
+        ce.clip_eval(len(mine), 3, 50, 5, (255, 448), lazy=True, arch="resnet101", seed=4100 + rank)
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        clk.mark("start")
+        r = ce.clip_eval(len(mine), frames + 1, 50, 5, (255, 448), lazy=True, arch="resnet101", time_ops=True, seed=4000 + rank)
+        clk.mark("end")
+    ms = max_over_ranks(r["ms"], dev)
+    total_frames = sum_over_ranks(r["frames"], dev)
+    return {"workload": "configs[3]: ResNet-101 + neck (stock torch), synthetic YouTube-VOS-shaped clips: 27 frames, 1..5 of F=5 objects, "
+                        "N=50, 255x448, eval.yaml 40x5; DMM_Model.inference_lazy; clips sharded clip % world == rank, no collective",
+            "clips": clips_total, "clips_per_gpu": len(mine), "clips_per_s": clips_total / (ms * 1e-3),
+            "frames_per_s": total_frames / (ms * 1e-3), "ms_per_frame_step_max_over_ranks": ms / frames,
+            "per_op_rank0": _shares(r["op_ms"]), "scaling": "weak (8 clips per GPU)", "clocks": clk.summary()}
+
+
+def leg_train(dev, local_rank, rank, world, steps=8):
+    """BASELINE configs[4]: train.py-shaped step, random-init ResNet-50, 4 clips x 3 frames per GPU (scripts/train/train_r50.sh),
+    matching layer in training mode with autograd, Adam; the data-parallel exchange is ONE all-reduce of all gradients
+    (a flat bucket; reference train.py:178-184 DDP, without its redundant per-parameter pass train.py:62-68)."""
+    from dmm_net_b200.sharding import max_over_ranks
+    ts = _load_example("synthetic_train_step")
+    with ClockSampler(local_rank) as clk:
+        clk.mark("start")
+        r = ts.train_loop("resnet50", 4, 3, 3, 50, (H, W), steps=steps, warmup=3, reduce="flat" if world > 1 else "none")
+        clk.mark("end")
+        ddp = ts.train_loop("resnet50", 4, 3, 3, 50, (H, W), steps=4, warmup=2, reduce="ddp") if world > 1 else None
+    step_ms = max_over_ranks(r["step_ms"], dev)
+    red_ms = max_over_ranks(r["reduce_ms"], dev)
+    out = {"workload": "configs[4]: train.py-shaped step, ResNet-50 + neck + conv decoder (stock torch, random init), 4 clips x 3 frames "
+                       "per GPU, N=50 F=3 256x448, train.yaml 10x5, K8/K5/K2/K1/K3/K4/K6 with autograd, fused Adam",
+           "step_ms": step_ms, "host_ms": r["host_ms"], "fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"], "opt_ms": r["opt_ms"],
+           "clips_per_s": world * 4 / (step_ms * 1e-3), "grad_bytes": r["grad_bytes"], "grad_tensors": r["n_grad_tensors"],
+           "exchange": r["reduce"], "exposed_allreduce_ms": red_ms if world > 1 else 0.0,
+           "allreduce": None, "scaling": "weak (4 clips per GPU)", "clocks": clk.summary(),
+           "note": "the step is bound by the host thread launching the stock-torch backbone kernels (host_ms ~ step_ms); the all-reduce "
+                   "runs after backward, fully exposed, and is timed by CUDA events around it"}
+    if world > 1:
+        bus = 2 * (world - 1) / world * r["grad_bytes"] / (red_ms * 1e-3) / 1e9 if red_ms > 0 else None
+        out["allreduce"] = {"collective": "NCCL all-reduce (AVG), one flat fp32 bucket", "bytes": r["grad_bytes"], "ms": red_ms,
+                            "bus_gbs": bus, "share_of_step": red_ms / step_ms}
+        out["torch_ddp_step_ms"] = max_over_ranks(ddp["step_ms"], dev)
+    return out
+
+
+def host_rooflines(host_masks, dev, threads):
+    """What bounds the host-buffer entry: streaming-read bandwidth of the pinned mask buffer with the packer's thread team
+    (every mask byte is read from host DRAM once, whichever route carries it) and the pinned host->device copy rate."""
+    import ctypes
+    from dmm_net_b200 import _lib
+    lib = _lib.load()
+    gbs = ctypes.c_double(0.0)
+    lib.dmm_host_read_bandwidth(ctypes.c_void_p(host_masks.data_ptr()), host_masks.numel() * 4, int(threads), 3, ctypes.byref(gbs))
+    dst = torch.empty_like(host_masks, device=dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dst.copy_(host_masks, non_blocking=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(2):
+        dst.copy_(host_masks, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    return gbs.value, 2 * host_masks.numel() * 4 / (a.elapsed_time(b) * 1e-3) / 1e9
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +327,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40, help="timed host-buffer steps (the pipeline drain at the end is amortised over them)")
     ap.add_argument("--secondary-steps", type=int, default=5, help="timed steps of the full-layer secondary metric (0: skip)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads for mask packing (0: cgroup-aware default)")
+    ap.add_argument("--legs", default="clip,eval,train", help="secondary legs (BASELINE configs[2..4]): comma list of clip,eval,train; '' = none")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -327,6 +438,15 @@ def main():
     e2e_val = world * Be * args.e2e_steps / (e2e_ms * 1e-3)
     d2h = (res_host.numel() + res_ms.numel()) * 4
 
+    # ---- what bounds e2e: host-DRAM streaming read (packer's thread team) and the pinned H2D copy rate, measured here -----
+    e2e_threads = args.e2e_threads or max(2, ops.host_threads() // world)
+    host_read_gbs, h2d_gbs = host_rooflines(host["prop_mask"], dev, e2e_threads)
+    if world > 1:
+        t = torch.tensor([host_read_gbs, h2d_gbs], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)                      # all ranks measured at the same time: aggregate rates
+        host_read_gbs, h2d_gbs = t.tolist()
+    e2e_gbs = e2e_val * MASK_BYTES_PER_MATCH / 1e9                    # mask bytes that left host DRAM per second, whole job
+
     # ---- secondary: the full layer incl. assignment-apply (K4), resident inputs, this rank only ------
     secondary = None
     if rank == 0 and args.secondary_steps > 0:
@@ -342,10 +462,36 @@ def main():
             b.record()
             torch.cuda.synchronize()
             ms_full = a.elapsed_time(b) / args.secondary_steps
-        secondary = {"full_layer_matches_per_s_per_gpu": B / (ms_full * 1e-3), "full_layer_ms_per_step": ms_full,
-                     "what": "MatchModel.forward_many incl. K4 assignment-apply writing full_outmask [B,O,H,W], resident inputs"}
+        secondary = {"full_layer": {"matches_per_s_per_gpu": B / (ms_full * 1e-3), "ms_per_step": ms_full,
+                                    "what": "MatchModel.forward_many incl. K4 assignment-apply writing full_outmask [B,O,H,W], resident inputs"}}
         del out_full
     h2d = e2e_info.get("h2d", 0)
+
+    # ---- secondary legs: BASELINE configs[2], [3], [4] (bounded; each with its own clocks window) ---------------------------
+    del pr, R
+    torch.cuda.empty_cache()
+    legs = [x for x in args.legs.split(",") if x]
+    leg_out = {}
+    for name in legs:
+        t_leg = time.perf_counter()
+        try:
+            if name == "clip" and world == 1:
+                leg_out["clip_r50"] = leg_clip_r50(dev, local_rank)
+            elif name == "eval":
+                leg_out["eval_r101"] = leg_eval_r101(dev, local_rank, rank, world)
+            elif name == "train":
+                leg_out["train"] = leg_train(dev, local_rank, rank, world)
+        except Exception as exc:                                      # a leg must never cost the headline line
+            import traceback
+            leg_out[name + "_error"] = f"{type(exc).__name__}: {exc}"
+            traceback.print_exc(file=sys.stderr)
+        for k in ("clip_r50", "eval_r101", "train"):
+            if k in leg_out and "wall_s" not in leg_out[k]:
+                leg_out[k]["wall_s"] = round(time.perf_counter() - t_leg, 1)
+        torch.cuda.empty_cache()
+    if secondary is None:
+        secondary = {}
+    secondary.update(leg_out)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -365,6 +511,16 @@ def main():
                     "host_threads": e2e_info.get("threads"), "problems_sent_as_fp32": e2e_info.get("raw"),
                     "host_pack_ms_per_step": None if e2e_info.get("pack_s") is None else 1e3 * e2e_info["pack_s"],
                     "route_seconds_per_problem(pack,dma)": e2e_info.get("est"),
+                    "roofline": {"bound": "host: every mask byte leaves host memory once, through the packing cores or through the copy engine",
+                                 "achieved_gbs": e2e_gbs, "host_dram_read_peak_gbs": host_read_gbs,
+                                 "pinned_h2d_peak_gbs": h2d_gbs,
+                                 "ceiling_gbs": host_read_gbs + h2d_gbs,
+                                 "frac_of_ceiling": e2e_gbs / (host_read_gbs + h2d_gbs) if host_read_gbs + h2d_gbs else None,
+                                 "ceiling_matches_per_s": (host_read_gbs + h2d_gbs) * 1e9 / MASK_BYTES_PER_MATCH,
+                                 "ceiling_model": "packed route <= what the packing threads can stream from host DRAM; raw route <= the pinned "
+                                                  "H2D rate of the copy engine; both run at once, so the ceiling is their sum (each measured alone)",
+                                 "how": f"dmm_host_read_bandwidth: {e2e_threads} threads per rank streaming the pinned proposal-mask buffer "
+                                        "(best of 3); H2D: 2 pinned copies of the same buffer, CUDA events; summed over ranks"},
                     "api": "MatchModel.forward_many_host: pinned host fp32 inputs; the host cores bit-pack most masks (bits "
                            "cross PCIe) while the copy engine DMAs the rest as fp32; features+scores H2D, R and match_score D2H"},
             "gpu_launches": launches,
@@ -378,9 +534,16 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "matches/s", "cores": threads, "kind": kind,
                                     "sample": f"{n} problems of the headline shape in {el:.1f} s, {what}"}
         prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(prof):
-            try:
-                line["roofline"]["traffic"] = json.load(open(prof)).get("traffic_bytes_per_match", 0) * B or None
+        if os.path.exists(prof):                                      # an ncu number (dram bytes per match of one capture): only
+            try:                                                      #   valid for the kernel source it was captured from
+                import hashlib
+                rec = json.load(open(prof))
+                src_sha = hashlib.sha256(open(os.path.join(ROOT, "dmm_net_b200", "csrc", "mask_iou.cu"), "rb").read()).hexdigest()
+                if rec.get("source_sha256") in (None, src_sha):
+                    line["roofline"]["traffic"] = rec.get("traffic_bytes_per_match", 0) * B or None
+                    line["roofline"]["traffic_source"] = rec.get("source")
+                else:
+                    line["roofline"]["traffic_source"] = "stale: mask_iou.cu changed since the ncu capture in profiles/k1_traffic.json"
             except Exception:
                 pass
         print(json.dumps(line), flush=True)
