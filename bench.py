@@ -280,20 +280,74 @@ def leg_train(dev, local_rank, rank, world, steps=8):
         ddp = ts.train_loop("resnet50", 4, 3, 3, 50, (H, W), steps=4, warmup=2, reduce="ddp") if world > 1 else None
     step_ms = max_over_ranks(r["step_ms"], dev)
     red_ms = max_over_ranks(r["reduce_ms"], dev)
+    skew_ms = max_over_ranks(r["skew_ms"], dev)
     out = {"workload": "configs[4]: train.py-shaped step, ResNet-50 + neck + conv decoder (stock torch, random init), 4 clips x 3 frames "
                        "per GPU, N=50 F=3 256x448, train.yaml 10x5, K8/K5/K2/K1/K3/K4/K6 with autograd, fused Adam",
            "step_ms": step_ms, "host_ms": r["host_ms"], "fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"], "opt_ms": r["opt_ms"],
            "clips_per_s": world * 4 / (step_ms * 1e-3), "grad_bytes": r["grad_bytes"], "grad_tensors": r["n_grad_tensors"],
            "exchange": r["reduce"], "exposed_allreduce_ms": red_ms if world > 1 else 0.0,
+           "rank_skew_wait_ms": skew_ms if world > 1 else 0.0,
            "allreduce": None, "scaling": "weak (4 clips per GPU)", "clocks": clk.summary(),
            "note": "the step is bound by the host thread launching the stock-torch backbone kernels (host_ms ~ step_ms); the all-reduce "
-                   "runs after backward, fully exposed, and is timed by CUDA events around it"}
+                   "runs after backward, fully exposed, and is timed by CUDA events around it; a 4-byte all-reduce right before it absorbs "
+                   "the wait for the slowest rank (rank_skew_wait_ms), so exposed_allreduce_ms is the transfer itself"}
     if world > 1:
         bus = 2 * (world - 1) / world * r["grad_bytes"] / (red_ms * 1e-3) / 1e9 if red_ms > 0 else None
         out["allreduce"] = {"collective": "NCCL all-reduce (AVG), one flat fp32 bucket", "bytes": r["grad_bytes"], "ms": red_ms,
                             "bus_gbs": bus, "share_of_step": red_ms / step_ms}
         out["torch_ddp_step_ms"] = max_over_ranks(ddp["step_ms"], dev)
     return out
+
+
+def leg_worker(name):
+    """`bench.py --leg-worker NAME`: one secondary leg in its OWN process group (spawned by rank 0 of the main run, under
+    torchrun when N > 1), so that nothing a leg does -- another model, another allocator state, a CUDA fault -- can cost the
+    headline line.  Rank 0 prints one JSON line tagged "leg"."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    t0 = time.perf_counter()
+    if name == "clip":
+        out = leg_clip_r50(dev, local_rank)
+    elif name == "eval":
+        out = leg_eval_r101(dev, local_rank, rank, world)
+    elif name == "train":
+        out = leg_train(dev, local_rank, rank, world)
+    else:
+        raise SystemExit(f"unknown leg {name}")
+    out["wall_s"] = round(time.perf_counter() - t0, 1)
+    if rank == 0:
+        print(json.dumps({"leg": name, "result": out}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_leg(name, world, index):
+    """Rank 0 of the main run: spawn the leg's process group on the same GPUs and read its JSON line back."""
+    cmd = [sys.executable]
+    if world > 1:
+        port = int(os.environ.get("MASTER_PORT", "29500")) + 101 + index
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                "--master-port", str(port)]
+    cmd += [os.path.join(ROOT, "bench.py"), "--leg-worker", name, "--gpus", str(world)]
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "ROLE_WORLD_SIZE",
+                        "GROUP_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT") and not k.startswith("TORCHELASTIC_")}
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
+    except subprocess.TimeoutExpired:
+        return {"error": "leg timed out after 600 s"}
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith('{"leg"'):
+            return json.loads(line)["result"]
+    tail = [x for x in r.stderr.splitlines() if x.strip() and "Warning" not in x][-6:]
+    return {"error": f"leg exited with code {r.returncode}", "stderr_tail": tail}
 
 
 def host_rooflines(host_masks, dev, threads):
@@ -328,6 +382,7 @@ def main():
     ap.add_argument("--secondary-steps", type=int, default=5, help="timed steps of the full-layer secondary metric (0: skip)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads for mask packing (0: cgroup-aware default)")
     ap.add_argument("--legs", default="clip,eval,train", help="secondary legs (BASELINE configs[2..4]): comma list of clip,eval,train; '' = none")
+    ap.add_argument("--leg-worker", default="", help="internal: run one secondary leg in this process group and print its JSON")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -336,6 +391,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.leg_worker:
+        leg_worker(args.leg_worker)
         return
 
     import torch.distributed as dist
@@ -398,7 +456,10 @@ def main():
     from dmm_net_b200.synth import default_cfg
     layer = MatchModel(default_cfg(MAX_ITER, PROJ_ITER, LR, SCORE_W), is_test=1)
     Be = min(B, 64)
-    host = {k: getattr(pr, k)[:Be].cpu().pin_memory() for k in ("prop_feat", "prop_mask", "tmpl_feat", "tmpl_mask", "prop_score")}
+    from dmm_net_b200 import hostmem
+    host, host_node = {}, None
+    for k in ("prop_feat", "prop_mask", "tmpl_feat", "tmpl_mask", "prop_score"):     # pinned, on the GPU's NUMA node when allowed
+        host[k], host_node = hostmem.pinned_near_gpu(getattr(pr, k)[:Be].cpu(), local_rank)
     res_host = torch.empty(Be, O, max(P, O + 1), pin_memory=True)
     res_ms = torch.empty(Be, O, pin_memory=True)
     e2e_info = {}
@@ -467,28 +528,25 @@ def main():
         del out_full
     h2d = e2e_info.get("h2d", 0)
 
-    # ---- secondary legs: BASELINE configs[2], [3], [4] (bounded; each with its own clocks window) ---------------------------
+    # ---- secondary legs: BASELINE configs[2], [3], [4] -- each in its own process group on the same GPUs (see leg_worker);
+    #      the ranks of this run free their memory and wait on the host (gloo), not on the GPU
     del pr, R
     torch.cuda.empty_cache()
-    legs = [x for x in args.legs.split(",") if x]
+    legs = [x for x in args.legs.split(",") if x and not (x == "clip" and world > 1)]
     leg_out = {}
-    for name in legs:
-        t_leg = time.perf_counter()
-        try:
-            if name == "clip" and world == 1:
-                leg_out["clip_r50"] = leg_clip_r50(dev, local_rank)
-            elif name == "eval":
-                leg_out["eval_r101"] = leg_eval_r101(dev, local_rank, rank, world)
-            elif name == "train":
-                leg_out["train"] = leg_train(dev, local_rank, rank, world)
-        except Exception as exc:                                      # a leg must never cost the headline line
-            import traceback
-            leg_out[name + "_error"] = f"{type(exc).__name__}: {exc}"
-            traceback.print_exc(file=sys.stderr)
-        for k in ("clip_r50", "eval_r101", "train"):
-            if k in leg_out and "wall_s" not in leg_out[k]:
-                leg_out[k]["wall_s"] = round(time.perf_counter() - t_leg, 1)
-        torch.cuda.empty_cache()
+    import datetime
+    del host
+    ctl = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=45)) if world > 1 and legs else None
+    if legs:
+        torch.cuda.synchronize()
+        if ctl is not None:
+            dist.barrier(group=ctl)
+        if rank == 0:
+            names = {"clip": "clip_r50", "eval": "eval_r101", "train": "train"}
+            for i, name in enumerate(legs):
+                leg_out[names.get(name, name)] = run_leg(name, world, i)
+        if ctl is not None:
+            dist.barrier(group=ctl)
     if secondary is None:
         secondary = {}
     secondary.update(leg_out)
@@ -509,6 +567,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "matches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "problems_per_step": Be, "host_bytes_packed_per_step": e2e_info.get("packed"),
                     "host_threads": e2e_info.get("threads"), "problems_sent_as_fp32": e2e_info.get("raw"),
+                    "host_buffers_numa_node": host_node,
                     "host_pack_ms_per_step": None if e2e_info.get("pack_s") is None else 1e3 * e2e_info["pack_s"],
                     "route_seconds_per_problem(pack,dma)": e2e_info.get("est"),
                     "roofline": {"bound": "host: every mask byte leaves host memory once, through the packing cores or through the copy engine",

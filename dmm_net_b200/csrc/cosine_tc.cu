@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
       const bool two = b0 + 1 < p.B;
       for (int kc = 0; kc < p.nK; ++kc, ++g) {
         const uint32_t s = g % kStages;
-        if (g >= kStages) mbar_wait(smem_u32(&raw_empty[s]), ((g / kStages) - 1u) & 1u);
+        if (g >= kStages) mbar_wait(smem_u32(&raw_empty[s]), ((g / kStages) - 1u) & 1u, 101);
         K2_STAMP(0, g);
         const uint32_t bar = smem_u32(&raw_full[s]);
         const uint32_t a_raw = stage0 + s * kStageBytes, b_raw = a_raw + kBytesA;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
       for (int kc = 0; kc < p.nK; ++kc, ++g) {
         if ((g & 1u) != grp) continue;
         const uint32_t s = g % kStages, l = g % kOpStages;
-        mbar_wait(smem_u32(&raw_full[s]), (g / kStages) & 1u);
+        mbar_wait(smem_u32(&raw_full[s]), (g / kStages) & 1u, 102);
         if (tid == 0) K2_STAMP(1, g);
         if (tid == 256) K2_STAMP(5, g);
         const uint32_t raw = stage0 + s * kStageBytes + (is_a ? 0u : kBytesA) + row_off;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
           nrm = fmaf(__uint_as_float(x[c].z), __uint_as_float(x[c].z), nrm);
           nrm = fmaf(__uint_as_float(x[c].w), __uint_as_float(x[c].w), nrm);
         }
-        if (g >= kOpStages) mbar_wait(smem_u32(&op_empty[l]), ((g / kOpStages) - 1u) & 1u);   // MMAs of chunk g-4 done
+        if (g >= kOpStages) mbar_wait(smem_u32(&op_empty[l]), ((g / kOpStages) - 1u) & 1u, 103);   // MMAs of chunk g-4 done
         if (tid == 0) K2_STAMP(2, g);
         if (is_a) tc_fence_after();
 #pragma unroll
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
         }
       }
       // hand the partial sum of squares to the epilogue (buffer `ab` is free once the epilogue of pair it-2 has arrived)
-      if (it >= 2) mbar_wait(smem_u32(&tmem_empty[ab]), ((it >> 1) - 1) & 1);
+      if (it >= 2) mbar_wait(smem_u32(&tmem_empty[ab]), ((it >> 1) - 1) & 1, 104);
       if (is_a) s_knorm2[ab][grp][row] = nrm; else s_qnorm2[ab][grp][row] = nrm;
       mbar_arrive(smem_u32(&norm_full[ab]));
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
     uint32_t g = 0;
     for (int it = 0; it < my_pairs; ++it) {
       const int ab = it & 1;
-      if (it >= 2) mbar_wait(smem_u32(&tmem_empty[ab]), ((it >> 1) - 1) & 1);
+      if (it >= 2) mbar_wait(smem_u32(&tmem_empty[ab]), ((it >> 1) - 1) & 1, 104);
       tc_fence_after();
       int grp = 0, in_grp = 0;                               // K group -> its own 32 accumulator columns
       for (int kc = 0; kc < p.nK; ++kc, ++g) {
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
         const bool first = in_grp == 0;
         if (++in_grp == p.per_group) { in_grp = 0; ++grp; }
         const uint32_t l = g % kOpStages;
-        mbar_wait(smem_u32(&op_full[l]), (g / kOpStages) & 1u);
+        mbar_wait(smem_u32(&op_full[l]), (g / kOpStages) & 1u, 105);
         K2_STAMP(4, g);
         tc_fence_after();
         const uint32_t a_hi = tmem_base + kOpCol0 + l * kOpCols, a_lo = a_hi + kKC;
@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) cosine_tc_kernel(const TcParams
       const int ab = it & 1;
       const int pair = blockIdx.x + it * gridDim.x;
       const int b = 2 * pair + m;
-      mbar_wait(smem_u32(&norm_full[ab]), (it >> 1) & 1);
-      mbar_wait(smem_u32(&tmem_full[ab]), (it >> 1) & 1);
+      mbar_wait(smem_u32(&norm_full[ab]), (it >> 1) & 1, 106);
+      mbar_wait(smem_u32(&tmem_full[ab]), (it >> 1) & 1, 107);
       tc_fence_after();
       float dot[kPadO];
 #pragma unroll

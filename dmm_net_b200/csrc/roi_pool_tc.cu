@@ -21,7 +21,7 @@
 //   roi_pool_tc_kernel persistent, warp-specialised, one CTA per SM; work item = (group, level, x segment, band of
 //                      rows), claimed from an atomic counter, big items first:
 //        warp 16 (1 lane) TMA: one cp.async.bulk.tensor.3d box [128 ch x 1 row x 32 px] (SWIZZLE_128B, zero fill past
-//                         W) per chunk into a 5-deep ring; only rows / x chunks inside the union window of the group's
+//                         W) per chunk into a 4-deep ring; only rows / x chunks inside the union window of the group's
 //                         ROIs are fetched;
 //        warps 0-7        split pass (two groups on alternate chunks): fp32 -> TF32 hi / lo, written to TENSOR MEMORY
 //                         (tcgen05.st; channel = TMEM lane) as the A operand;
@@ -50,9 +50,17 @@ constexpr int kC = 128;                         // channels = MMA M (the referen
 constexpr int kNR = 64;                         // ROI slots per group = MMA N
 constexpr int kKC = 32;                         // floats per K chunk (one 128-byte swizzle row)
 #ifndef K5_STAGES
-#define K5_STAGES 5
+#define K5_STAGES 4
 #endif
-constexpr int kStages = K5_STAGES;              // raw fp32 ring (what the TMA keeps in flight: 5 x 16 KB)
+// Raw fp32 ring (what the TMA keeps in flight: 4 x 16 KB; measured: 2, 3 and 5 stages run at the same speed).  MUST BE EVEN:
+// the two converter groups take alternate chunks, and a waiter tests the PARITY of an mbarrier phase.  With an odd ring
+// the groups alternate on every stage, so a group's consecutive visits to a stage are two phases apart -- same parity --
+// and its wait for chunk g+2*kStages passes as soon as phase g has completed, i.e. possibly BEFORE chunk g+kStages (the
+// other group's) has even landed: TMA completions are not ordered.  Seen once per ~500 calls on 8 GPUs under NVLink
+// traffic (5 stages): stale data converted, arrivals on the wrong phase, pipeline stall.  With an even ring a stage always
+// belongs to the same group and consecutive visits are consecutive phases.
+constexpr int kStages = K5_STAGES;
+static_assert(kStages % 2 == 0, "raw ring depth must be even (see above)");
 constexpr int kOpStages = 4;                    // A operand ring in TMEM
 constexpr int kMetaRing = 16;                   // per-chunk metadata (producer leads the MMA warp by < 10 chunks)
 constexpr int kItemRing = 4;

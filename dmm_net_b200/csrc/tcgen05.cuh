@@ -46,14 +46,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int id 
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-#ifdef DMM_TC_DEBUG   // debug builds name the barrier that never completed
+    // ~2 s (debug builds: 0.2 s).  The message names the barrier: it is all that is left of the kernel after the trap.
+#ifdef DMM_TC_DEBUG
     if (clock64() - t0 > 400000000LL) {
-      if ((threadIdx.x & 31) == 0) printf("mbar timeout: block %d warp %d barrier id %d parity %u\n", blockIdx.x, threadIdx.x >> 5, id, parity);
+#else
+    if (clock64() - t0 > 4000000000LL) {
+#endif
+      if ((threadIdx.x & 31) == 0)
+        printf("libdmm_b200: mbarrier wait timed out (block %d warp %d barrier id %d parity %u) -- pipeline protocol bug, trapping\n",
+               blockIdx.x, threadIdx.x >> 5, id, parity);
       __trap();
     }
-#else
-    if (clock64() - t0 > 4000000000LL) __trap();
-#endif
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {

@@ -1024,7 +1024,9 @@ def host_threads() -> int:
 def _pinned(key, shape, dtype):
     t = _PINNED.get(key)
     if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-        t = torch.empty(shape, dtype=dtype).pin_memory()
+        from . import hostmem
+        with hostmem.prefer_node(hostmem.gpu_numa_node(torch.cuda.current_device())):   # staging next to the GPU's socket
+            t = torch.empty(shape, dtype=dtype).pin_memory()
         _PINNED[key] = t
     return t
 

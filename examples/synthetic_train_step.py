@@ -93,6 +93,14 @@ class FlatGradBucket:
         import torch.distributed as dist
         dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
 
+    def rendezvous(self):
+        """4-byte all-reduce: returns (on the stream) once every rank has finished its backward -- separates the wait for the
+        slowest rank from the time of the gradient exchange itself"""
+        import torch.distributed as dist
+        if not hasattr(self, "_probe"):
+            self._probe = torch.zeros(1, device=self.flat.device)
+        dist.all_reduce(self._probe)
+
     @property
     def nbytes(self):
         return self.flat.numel() * 4
@@ -134,11 +142,11 @@ def train_loop(arch="resnet50", clips=4, frames=3, objects=3, proposals=50, size
     gen = torch.Generator(device=dev).manual_seed(7000 + rank + seed_offset)
     valid = torch.ones(B, Fo, device=dev)
     hist = []
-    rec = {k: [] for k in ("step_ms", "host_ms", "fwd_ms", "bwd_ms", "reduce_ms", "opt_ms")}
+    rec = {k: [] for k in ("step_ms", "host_ms", "fwd_ms", "bwd_ms", "skew_ms", "reduce_ms", "opt_ms")}
     E = lambda: torch.cuda.Event(enable_timing=True)
     pending = []
     for step in range(warmup + steps):
-        e0, e1, e2, e3, e4 = E(), E(), E(), E(), E()
+        e0, e1, e2, e2b, e3, e4 = E(), E(), E(), E(), E(), E()
         t0 = time.perf_counter()
         e0.record()
         if bucket is not None:
@@ -183,14 +191,17 @@ def train_loop(arch="resnet50", clips=4, frames=3, objects=3, proposals=50, size
         loss_total.backward()                                        # "ddp": bucketed NCCL all-reduce overlapped with this
         e2.record()
         if reduce == "flat":
+            bucket.rendezvous()                                      # wait for the slowest rank (timed separately)
+        e2b.record()
+        if reduce == "flat":
             bucket.all_reduce_mean()                                 # ONE all-reduce of every gradient (NCCL, NVLink)
         e3.record()
         opt.step()
         e4.record()
         host_ms = 1e3 * (time.perf_counter() - t0)
-        pending.append((step, e0, e1, e2, e3, e4, host_ms, loss_total.detach(), torch.stack(hard_iou).mean()))
+        pending.append((step, e0, e1, e2, e2b, e3, e4, host_ms, loss_total.detach(), torch.stack(hard_iou).mean()))
     torch.cuda.synchronize()
-    for step, e0, e1, e2, e3, e4, host_ms, loss, hi in pending:
+    for step, e0, e1, e2, e2b, e3, e4, host_ms, loss, hi in pending:
         hist.append((float(loss), float(hi)))
         assert hist[-1][0] == hist[-1][0], "loss is NaN"
         if step < warmup:
@@ -199,7 +210,8 @@ def train_loop(arch="resnet50", clips=4, frames=3, objects=3, proposals=50, size
         rec["host_ms"].append(host_ms)
         rec["fwd_ms"].append(e0.elapsed_time(e1))
         rec["bwd_ms"].append(e1.elapsed_time(e2))
-        rec["reduce_ms"].append(e2.elapsed_time(e3))
+        rec["skew_ms"].append(e2.elapsed_time(e2b))
+        rec["reduce_ms"].append(e2b.elapsed_time(e3))
         rec["opt_ms"].append(e3.elapsed_time(e4))
     g = [p.grad for p in params if p.grad is not None]
     assert len(g) > 0 and all(torch.isfinite(x).all() for x in g)
@@ -224,7 +236,7 @@ def run(args):
     if rank == 0:
         print(f"{args.arch} ranks={world} reduce={r['reduce']} {r['clips']} clips x {r['frames']} frames {args.size[0]}x{args.size[1]} "
               f"P={r['proposals']} F={r['objects']}: median step {r['step_ms']:.1f} ms (host {r['host_ms']:.1f}; fwd {r['fwd_ms']:.1f} "
-              f"bwd {r['bwd_ms']:.1f} reduce {r['reduce_ms']:.2f} opt {r['opt_ms']:.2f}); loss {hist[0][0]:.4f} -> {hist[-1][0]:.4f}; "
+              f"bwd {r['bwd_ms']:.1f} skew {r['skew_ms']:.2f} reduce {r['reduce_ms']:.2f} opt {r['opt_ms']:.2f}); loss {hist[0][0]:.4f} -> {hist[-1][0]:.4f}; "
               f"hard IoU {hist[-1][1]:.4f}; {r['n_grad_tensors']} parameter tensors with gradients, {r['grad_bytes'] / 1e6:.1f} MB")
     if world > 1:
         dist.destroy_process_group()
