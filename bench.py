@@ -528,6 +528,45 @@ def main():
         del out_full
     h2d = e2e_info.get("h2d", 0)
 
+    # ---- secondary: the layer in TRAINING mode (train.yaml 10x5, targets given -> match loss), forward + backward, resident -----
+    if rank == 0 and args.secondary_steps > 0:
+        try:
+            layer_tr = MatchModel(default_cfg(10, 5, LR, SCORE_W), is_test=0)
+            targets = (pr.tmpl_mask > 0.3).float()
+            pf = pr.prop_feat.clone().requires_grad_(True)
+            tf = pr.tmpl_feat.clone().requires_grad_(True)
+
+            def train_step():
+                out = layer_tr.forward_many(pf, pr.prop_mask, tf, pr.tmpl_mask, pr.prop_score, targets)
+                (out["full_outmask"].mean() + out["match_score"].sum() + out["cost_loss"].sum()).backward()
+                pf.grad = tf.grad = None
+
+            train_step()
+            timer = ops.KernelTimer()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ops.set_kernel_timer(timer)
+            a.record()
+            for _ in range(3):
+                train_step()
+            b.record()
+            ops.set_kernel_timer(None)
+            op_ms = {k: v / 3 for k, v in timer.totals().items()}
+            ms_tr = a.elapsed_time(b) / 3
+            k1_tr = op_ms.get("K1 mask_iou", 0.0)
+            bytes_tr = (P + 2 * O) * H * W * 4 * B                       # proposals + previous masks + targets, each row once
+            peak_hbm, _ = measured_peaks()
+            secondary["train_layer"] = {
+                "what": "MatchModel.forward_many in training mode (targets -> match loss; K2, K1 with the targets as second template set in "
+                        "ONE pass over 70 rows, K3 fwd+bwd, K4 fwd+bwd, K2 bwd), forward + backward, resident inputs",
+                "matches_per_s_per_gpu": B / (ms_tr * 1e-3), "ms_per_step_fwd_bwd": ms_tr, "forward_op_ms": {k: round(v, 3) for k, v in op_ms.items()},
+                "k1_roofline": {"algorithmic_bytes_per_launch": bytes_tr, "kernel_ms_incl_finalize": k1_tr,
+                                "achieved_gbs": bytes_tr / (k1_tr * 1e-3) / 1e9 if k1_tr else None,
+                                "frac": bytes_tr / (k1_tr * 1e-3) / 1e9 / peak_hbm if k1_tr else None}}
+            del targets, pf, tf
+        except Exception as exc:
+            secondary["train_layer"] = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- secondary legs: BASELINE configs[2], [3], [4] -- each in its own process group on the same GPUs (see leg_worker);
     #      the ranks of this run free their memory and wait on the host (gloo), not on the GPU
     del pr, R

@@ -52,7 +52,9 @@ SIGNATURES = {
                                   _vp]),
     "dmm_roi_mean_pool_workspace_bytes": (_sz, [POINTER(c_int), POINTER(c_int), _i, _i, _i]),
     "dmm_roi_mean_pool": (_i, [POINTER(c_void_p), POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, _vp, _vp, _sz, _i, _vp]),
-    "dmm_roi_mean_pool_bwd": (_i, [_vp, POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, POINTER(c_void_p), _vp]),
+    "dmm_roi_mean_pool_bwd_workspace_bytes": (_sz, [POINTER(c_int), POINTER(c_int), _i, _i, _i]),
+    "dmm_roi_mean_pool_bwd": (_i, [_vp, POINTER(c_int), POINTER(c_int), _i, _i, _vp, _i, POINTER(c_void_p), _vp, _sz, _i,
+                                   POINTER(c_int), _vp]),
     "dmm_mask_pyramid_level_size": (_i, [_i, _i, _i, POINTER(c_int), POINTER(c_int)]),
     "dmm_mask_pyramid": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, POINTER(c_void_p), _vp]),
     "dmm_mask_pyramid_bwd": (_i, [POINTER(c_void_p), _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

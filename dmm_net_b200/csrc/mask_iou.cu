@@ -249,10 +249,19 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsThreads) : "memory"); }
 
-template <int TO>
+// ROWS / STAGES: 64 rows x 3 stages (64 KB each) is the inference shape (P + O <= 64, O <= 16).  Training adds the targets as
+// a second template set -- 50 + 10 + 10 = 70 rows, 20 template rows at the headline shape -- which used to fall back to two
+// passes that read the proposals twice (1.71x the algorithmic traffic); the wide instantiation (96 rows x 2 stages of
+// 96 KB, up to 32 template rows) takes it in ONE pass.
+template <int TO, int ROWS = kMaxRows, int STAGES = 3>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorMap tm_prop,
                             const __grid_constant__ CUtensorMap tm_tmpl, const __grid_constant__ CUtensorMap tm_tmpl2) {
+  constexpr int kStages = STAGES;                                 // shadows the file-level default inside this kernel
+  constexpr int kStageFloats = ROWS * kChunkPx;
+  constexpr int kTmaUnits = ROWS * 2 / kTmaConsWarps;
+  constexpr int kTOcap = TO <= kTileO ? kTileO : 32;              // template rows the reduction buffer holds
+  constexpr bool kWide = ROWS > kMaxRows;
   // PERSISTENT: one CTA per SM claims work items (problem b, pixel slab s) from an atomic counter.  The stage ring
   // and its mbarrier phases run on across items, so the producer is already filling the next item's stages while the
   // consumers reduce and write the previous item's counters: no pipeline fill/drain per slab (with one CTA per SM
@@ -260,8 +269,8 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
   constexpr int TH = TO / 2;                                      // template counters per warp half
   extern __shared__ unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ uint32_t bits[2][2][kMaxRows + kTileO][4];
-  __shared__ int red[kTileO * kMaxRows + kMaxRows];
+  __shared__ uint32_t bits[2][2][ROWS + kTileO][4];
+  __shared__ int red[kTOcap * kMaxRows + ROWS];
   __shared__ __align__(8) unsigned long long full_bar[kStages];
   __shared__ __align__(8) unsigned long long empty_bar[kStages];
   __shared__ int stage_item[kStages];   // work item of the chunk in each stage (-1: stop), written by the producer
@@ -272,7 +281,7 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
   const bool two = p.tmpl2 != nullptr;
   const int n_items = p.S * p.B_items;
 
-  for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kTmaThreads) red[i] = 0;
+  for (int i = tid; i < kTOcap * kMaxRows + ROWS; i += kTmaThreads) red[i] = 0;
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < kStages; ++st) {
@@ -327,7 +336,7 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
   int acc[TH][2];
 #pragma unroll
   for (int o = 0; o < TH; ++o) acc[o][0] = acc[o][1] = 0;
-  int area0 = 0, area1 = 0;
+  int area0 = 0, area1 = 0, area2 = 0;
   while (true) {
     const unsigned st = g % kStages, buf = g & 1u;
     mbar_wait(smem_u32(&full_bar[st]), (g / kStages) & 1u);
@@ -359,6 +368,7 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
       if (half == 0) {
         area0 += __popc(b0);
         area1 += __popc(b1);
+        if (kWide) area2 += __popc(bits[buf][grp_b][min(lane + 64, ROWS + kTileO - 1)][word_b]);   // rows 64..95 (template rows)
       }
 #pragma unroll
       for (int o = 0; o < TH; ++o) {
@@ -382,10 +392,11 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
       acc[o][0] = acc[o][1] = 0;
     }
     if (half == 0) {
-      atomicAdd(&red[kTileO * kMaxRows + lane], area0);
-      atomicAdd(&red[kTileO * kMaxRows + lane + 32], area1);
+      atomicAdd(&red[kTOcap * kMaxRows + lane], area0);
+      atomicAdd(&red[kTOcap * kMaxRows + lane + 32], area1);
+      if (kWide && lane + 64 < ROWS) atomicAdd(&red[kTOcap * kMaxRows + lane + 64], area2);
     }
-    area0 = area1 = 0;
+    area0 = area1 = area2 = 0;
     consumer_barrier();
     const int b = item / p.S, s = item - b * p.S;
     int* out = p.ws + ((long long)b * p.S + s) * p.cnt;
@@ -395,10 +406,10 @@ mask_iou_partial_tma_kernel(const IouParams p, const __grid_constant__ CUtensorM
     }
     int* area_t = out + p.Otot * p.P;
     int* area_p = area_t + p.Otot;
-    for (int i = tid; i < ocnt; i += kTmaConsThreads) area_t[i] = red[kTileO * kMaxRows + pcnt + i];
-    for (int i = tid; i < pcnt; i += kTmaConsThreads) area_p[i] = red[kTileO * kMaxRows + i];
+    for (int i = tid; i < ocnt; i += kTmaConsThreads) area_t[i] = red[kTOcap * kMaxRows + pcnt + i];
+    for (int i = tid; i < pcnt; i += kTmaConsThreads) area_p[i] = red[kTOcap * kMaxRows + i];
     consumer_barrier();
-    for (int i = tid; i < kTileO * kMaxRows + kMaxRows; i += kTmaConsThreads) red[i] = 0;
+    for (int i = tid; i < kTOcap * kMaxRows + ROWS; i += kTmaConsThreads) red[i] = 0;
     // the next epilogue's atomics come after at least one more chunk barrier: the zeroing above is ordered before them
   }
 }
@@ -435,16 +446,22 @@ bool make_map(CUtensorMap* m, const float* base, long long bs, int B, int rows, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int TO>
+template <int TO, int ROWS = kMaxRows, int STAGES = 3>
 int launch_tma(const IouParams& kp, const CUtensorMap& mp, const CUtensorMap& mt, const CUtensorMap& mt2, dim3 grid,
                cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(mask_iou_partial_tma_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kTmaDynSmem);
+  constexpr size_t dyn = (size_t)STAGES * ROWS * kChunkPx * sizeof(float) + 128;
+  cudaError_t e = cudaFuncSetAttribute(mask_iou_partial_tma_kernel<TO, ROWS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)dyn);
   if (e != cudaSuccess) { set_last_cuda_error((int)e); return DMM_ERR_CUDA; }
   const long long items = (long long)grid.x * grid.y;   // S * B work items, one persistent CTA per SM walks them
   const int nctas = (int)(items < kNumSMs ? items : kNumSMs);
-  mask_iou_partial_tma_kernel<TO><<<nctas, kTmaThreads, kTmaDynSmem, st>>>(kp, mp, mt, mt2);
+  mask_iou_partial_tma_kernel<TO, ROWS, STAGES><<<nctas, kTmaThreads, dyn, st>>>(kp, mp, mt, mt2);
   return check_launch();
+}
+
+constexpr int kWideRows = 96, kWideTO = 32;     // the wide single-pass tile of the TMA kernel (training: targets ride along)
+inline bool wide_shape(int P, int Otot) {
+  return P <= kMaxRows && Otot <= kWideTO && P + Otot <= kWideRows && (P + Otot > kMaxRows || Otot > kTileO);
 }
 
 struct FinParams {
@@ -502,11 +519,12 @@ struct Plan {
   int PT, OT, n_ptiles, n_otiles, S, n_chunks, chunks_per_slab, cnt, Otot;
 };
 
-Plan make_plan(int B, int P, int O, int HW, int two) {
+Plan make_plan(int B, int P, int O, int HW, int two, bool wide = false) {
   Plan pl;
   pl.Otot = O * (two ? 2 : 1);
   pl.OT = pl.Otot < kTileO ? pl.Otot : kTileO;
   pl.PT = P < kMaxRows - pl.OT ? P : kMaxRows - pl.OT;
+  if (wide) { pl.OT = pl.Otot; pl.PT = P; }     // one tile of <= 96 rows (TMA kernel only)
   if (pl.OT < 1) pl.OT = 1;
   if (pl.PT < 1) pl.PT = 1;
   pl.n_ptiles = (P + pl.PT - 1) / pl.PT;
@@ -534,7 +552,13 @@ using namespace dmm;
 extern "C" size_t dmm_mask_iou_workspace_bytes(int B, int P, int O, int HW, int two_template_sets) {
   if (B <= 0 || P <= 0 || O <= 0 || HW <= 0) return 0;
   const Plan pl = make_plan(B, P, O, HW, two_template_sets);
-  return align_up((size_t)B * pl.S * pl.cnt * sizeof(int), 256) + 256;   // + the persistent kernel's work counter
+  size_t bytes = (size_t)B * pl.S * pl.cnt * sizeof(int);
+  if (wide_shape(P, pl.Otot)) {                 // which of the two plans runs is decided at launch (alignment, tensor maps)
+    const Plan pw = make_plan(B, P, O, HW, two_template_sets, true);
+    const size_t bw = (size_t)B * pw.S * pw.cnt * sizeof(int);
+    if (bw > bytes) bytes = bw;
+  }
+  return align_up(bytes, 256) + 256;            // + the persistent kernel's work counter
 }
 
 static int run_pairwise(const float* prop, const float* const* prop_ptrs, int ptrs_aligned16, long long prop_bstride,
@@ -549,11 +573,27 @@ static int run_pairwise(const float* prop, const float* const* prop_ptrs, int pt
   if (iou2 && !tmpl2) return DMM_ERR_INVALID_ARGUMENT;
   if (B > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
   const int two = tmpl2 != nullptr;
-  const Plan pl = make_plan(B, P, O, HW > 0 ? HW : 1, two);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto aligned16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  const bool vec = (HW % 4 == 0) && (prop_ptrs ? ptrs_aligned16 != 0 : aligned16(prop)) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
+                   (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
+  // Staging path: the TMA ring is the default whenever it applies (aligned rows, single tile, tensor maps available);
+  // measured on par with / slightly ahead of the LDG pipeline (profiles/README.md).  DMM_K1_IMPL=ldg forces the
+  // LDG kernel (read-only environment lookup, used by the A/B parity test).
+  const char* impl = getenv("DMM_K1_IMPL");
+  const bool tma_ok = vec && !prop_ptrs && !(impl && impl[0] == 'l') && HW >= kChunkPx;
+  CUtensorMap mp, mt, mt2;
+  bool maps = false;
+  if (tma_ok) {
+    maps = make_map(&mp, prop, prop_bstride, B, P, HW) && make_map(&mt, tmpl, tmpl_bstride, B, O, HW);
+    if (maps && two) maps = make_map(&mt2, tmpl2, tmpl2_bstride, B, O, HW);
+    if (maps && !two) mt2 = mt;
+  }
+  const bool wide = maps && wide_shape(P, O * (two ? 2 : 1));
+  const Plan pl = make_plan(B, P, O, HW > 0 ? HW : 1, two, wide);
   const size_t counts_bytes = align_up((size_t)B * pl.S * pl.cnt * sizeof(int), 256);
   if (workspace_bytes < counts_bytes + 256) return DMM_ERR_WORKSPACE_TOO_SMALL;
   if (pl.n_ptiles * pl.n_otiles > 65535) return DMM_ERR_UNSUPPORTED_SHAPE;
-  cudaStream_t st = (cudaStream_t)stream;
 
   IouParams kp;
   kp.item_counter = (int*)((char*)workspace + counts_bytes);
@@ -569,28 +609,19 @@ static int run_pairwise(const float* prop, const float* const* prop_ptrs, int pt
   if (HW == 0) {  // empty masks: every count is 0 -> IoU 0/(0+1e-6) = 0; skip the streaming kernel
     DMM_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)B * pl.S * pl.cnt * sizeof(int), st));
   }
-  auto aligned16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
-  const bool vec = (HW % 4 == 0) && (prop_ptrs ? ptrs_aligned16 != 0 : aligned16(prop)) && aligned16(tmpl) && (!two || aligned16(tmpl2)) &&
-                   (prop_bstride % 4 == 0) && (tmpl_bstride % 4 == 0) && (!two || tmpl2_bstride % 4 == 0);
   dim3 grid(pl.S, B, pl.n_ptiles * pl.n_otiles);
   const int to = pl.OT <= 4 ? 4 : (pl.OT <= 8 ? 8 : (pl.OT <= 12 ? 12 : 16));
-  // Staging path: the TMA ring is the default whenever it applies (aligned rows, single tile, tensor maps available);
-  // measured on par with / slightly ahead of the LDG pipeline (profiles/README.md).  DMM_K1_IMPL=ldg forces the
-  // LDG kernel (read-only environment lookup, used by the A/B parity test).
-  const char* impl = getenv("DMM_K1_IMPL");
-  bool use_tma = vec && !prop_ptrs && !(impl && impl[0] == 'l') && pl.n_ptiles == 1 && pl.n_otiles == 1 && HW >= kChunkPx;
-  CUtensorMap mp, mt, mt2;
-  if (use_tma) {
-    use_tma = make_map(&mp, prop, prop_bstride, B, P, HW) && make_map(&mt, tmpl, tmpl_bstride, B, O, HW);
-    if (use_tma && two) use_tma = make_map(&mt2, tmpl2, tmpl2_bstride, B, O, HW);
-    if (use_tma && !two) mt2 = mt;
-  }
+  const bool use_tma = maps && pl.n_ptiles == 1 && pl.n_otiles == 1;
   int rc = DMM_OK;
   if (HW == 0) {
   } else if (use_tma) {
     DMM_CUDA_TRY(cudaMemsetAsync(kp.item_counter, 0, sizeof(int), st));
-    rc = to == 4 ? launch_tma<4>(kp, mp, mt, mt2, grid, st) : to == 8 ? launch_tma<8>(kp, mp, mt, mt2, grid, st)
-       : to == 12 ? launch_tma<12>(kp, mp, mt, mt2, grid, st) : launch_tma<16>(kp, mp, mt, mt2, grid, st);
+    if (wide)
+      rc = pl.OT <= 20 ? launch_tma<20, kWideRows, 2>(kp, mp, mt, mt2, grid, st)
+         : pl.OT <= 24 ? launch_tma<24, kWideRows, 2>(kp, mp, mt, mt2, grid, st) : launch_tma<32, kWideRows, 2>(kp, mp, mt, mt2, grid, st);
+    else
+      rc = to == 4 ? launch_tma<4>(kp, mp, mt, mt2, grid, st) : to == 8 ? launch_tma<8>(kp, mp, mt, mt2, grid, st)
+         : to == 12 ? launch_tma<12>(kp, mp, mt, mt2, grid, st) : launch_tma<16>(kp, mp, mt, mt2, grid, st);
   } else {
 #define DMM_LAUNCH(V, T) mask_iou_partial_kernel<V, T><<<grid, kThreads, 0, st>>>(kp)
     if (vec) {

@@ -232,15 +232,38 @@ extern "C" int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], co
   return check_launch();
 }
 
-extern "C" int dmm_roi_mean_pool_bwd(const float* g_out, const int Hl[4], const int Wl[4], int N, int C,
-                                     const float* rois, int R, float* const g_feat[4], void* stream) {
+namespace dmm {
+size_t roi_pool_bwd_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R);
+int roi_pool_bwd_try_launch(const float* g_out, const int Hl[4], const int Wl[4], int N, int C, const float* rois, int R,
+                            float* const g_feat[4], void* workspace, size_t workspace_bytes, cudaStream_t st);
+}  // namespace dmm
+
+extern "C" size_t dmm_roi_mean_pool_bwd_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R) {
+  if (!Hl || !Wl) return 0;
+  return roi_pool_bwd_workspace_bytes(Hl, Wl, N, C, R);
+}
+
+// impl: 0 = auto (deterministic gather when a workspace is given and the shapes fit: g_feat is then fully OVERWRITTEN;
+// otherwise the atomic scatter, which ACCUMULATES into g_feat -- the caller zero-initialises it), 1 = atomic scatter only,
+// 2 = deterministic gather required.  *wrote_all (optional) tells which of the two happened (1: overwritten).
+extern "C" int dmm_roi_mean_pool_bwd(const float* g_out, const int Hl[4], const int Wl[4], int N, int C, const float* rois, int R,
+                                     float* const g_feat[4], void* workspace, size_t workspace_bytes, int impl, int* wrote_all,
+                                     void* stream) {
   PoolParams kp; size_t smem, tsmem;
   int rc = fill(kp, Hl, Wl, N, C, rois, R, smem, tsmem);
   if (rc) return rc;
+  if (impl < 0 || impl > 2) return DMM_ERR_INVALID_ARGUMENT;
+  if (wrote_all) *wrote_all = 0;
   if (R == 0 || C == 0) return DMM_OK;
   if (!g_feat || !rois || !g_out) return DMM_ERR_INVALID_ARGUMENT;
   for (int l = 0; l < 4; ++l) { if (!g_feat[l]) return DMM_ERR_INVALID_ARGUMENT; kp.gfeat[l] = g_feat[l]; }
   kp.gout = g_out;
+  if (impl != 1) {
+    rc = roi_pool_bwd_try_launch(g_out, Hl, Wl, N, C, rois, R, g_feat, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc == DMM_OK) { if (wrote_all) *wrote_all = 1; return DMM_OK; }
+    if (rc > 0) return rc;
+    if (impl == 2) return DMM_ERR_UNSUPPORTED_SHAPE;
+  }
   if (tsmem) {
     DMM_CUDA_TRY(cudaFuncSetAttribute(roi_mean_pool_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     roi_mean_pool_kernel<true, true><<<dim3(R, 4), kThreads, tsmem, (cudaStream_t)stream>>>(kp);

@@ -115,6 +115,8 @@ struct TcPool {
   int btab_stride;
   float* partial;  // [Gb*items_per_group][64][128]
   long long* trace;  // debug builds (DMM_TC_DEBUG + DMM_K5_TRACE_FILE): (event, clock64) pairs of CTA 0
+  int tables_only;   // backward: weight tables (wyT, wx) for EVERY level, no B tiles / ranges
+  int C;             // channels (the contraction kernel needs 128; the backward gather takes any)
 };
 
 struct Item {      // what the producer publishes per work item (shared memory ring)
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(1024) tc_group_kernel(const TcPool p) {
   for (int i = tid; i < p.R; i += 1024) {
     const int n = (int)p.rois[(long long)i * 5];
     if (n >= 0 && n < p.N) atomicAdd(&cnt[n], 1);
-    else {                                                  // ROIs of no frame pool to zero (as the SIMT kernel)
+    else if (p.out) {                                       // ROIs of no frame pool to zero (as the SIMT kernel)
       float* o = p.out + (long long)i * 4 * kC;
       for (int c = 0; c < 4 * kC; ++c) o[c] = 0.f;
     }
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(256) tc_weights_kernel(const TcPool p) {
   const int g = blockIdx.x, l = blockIdx.y, tid = threadIdx.x;
   if (g >= p.hdr[0]) return;
   const LevelInfo lv = p.lv[l];
-  if (lv.mode == MODE_NONE) return;
+  if (lv.mode == MODE_NONE && !p.tables_only) return;
   const int H = lv.H, W = lv.W;
   float* wy = wsm;
   float* wx = wsm + kNR * H;
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(256) tc_weights_kernel(const TcPool p) {
   float* wxg = tab + lv.wx_off;                               // [64][Wp]
   for (int i = tid; i < H * kNR; i += 256) { const int y = i / kNR, r = i % kNR; wyT[i] = wy[r * H + y]; }
   for (int i = tid; i < kNR * lv.Wp; i += 256) { const int r = i / lv.Wp, x = i % lv.Wp; wxg[i] = x < W ? wx[r * W + x] : 0.f; }
+  if (p.tables_only) return;
   // The MMA's B operand for every 32-element chunk of the (virtual) row, exactly as shared memory wants it: 64 rows (ROI
   // slots) x 128 bytes, 16-byte chunk c of row r at ((c ^ (r & 7)) << 4), TF32 hi tile then lo tile.  Built once per
   // (group, level) here; the contraction kernel only bulk-copies it (every band of the level reuses it from L2).
@@ -761,7 +764,7 @@ bool make_plan(const int Hl[4], const int Wl[4], int N, int C, int R, Plan& pl) 
     lv.item0 = item0; item0 += lv.items;
   }
   kp.items_per_group = item0;
-  kp.N = N; kp.R = R;
+  kp.N = N; kp.R = R; kp.C = C; kp.tables_only = 0;
   kp.Gb = std::min(N, R) + R / kNR;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
@@ -778,6 +781,218 @@ bool make_plan(const int Hl[4], const int Wl[4], int N, int C, int R, Plan& pl) 
   return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward: gF[n, c, y, x] = sum over the frame's ROIs r of  gout[r, l*C + c] * wy[r, y] * wx[r, x]
+// A GATHER over the ROIs of the frame in bucket order -- every gradient element is written exactly once, by one thread,
+// with a fixed summation order: deterministic, no atomics, no zero-initialised output (the forward's SIMT sibling
+// scattered with atomicAdd).  CTA = (frame, level, band of rows, chunk of <= 128 channels); per row the ROIs whose wy is
+// non-zero are compacted and A[r][c] = gout[r][c] * wy[r][y] staged once; lanes run along x (coalesced stores), each
+// thread carries 8 channels: 8 FMAs per (wx load + two broadcast LDS.128).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 256;
+constexpr int kBwdCT = 8;                       // channels per thread
+
+struct BwdParams {
+  TcPool tp;                                    // groups, perm, weight tables, level shapes
+  const float* gout;                            // [R][4*C]
+  float* gfeat[4];
+  int rows_per_band[4], nband[4], band0[4];     // CTA decomposition per level
+};
+
+__global__ void __launch_bounds__(kBwdThreads) roi_pool_bwd_kernel(const BwdParams bp) {
+  extern __shared__ float bsm[];
+  const TcPool& p = bp.tp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // decode (level, band) from blockIdx.x, frame from blockIdx.y, channel chunk from blockIdx.z
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) if ((int)blockIdx.x >= bp.band0[k]) l = k;
+  const int band = blockIdx.x - bp.band0[l], n = blockIdx.y, c0 = blockIdx.z * kC;
+  const LevelInfo& lv = p.lv[l];
+  const int H = lv.H, W = lv.W, Wp = lv.Wp, C = p.C;
+  const int cn = min(kC, C - c0);
+  const int y0 = band * bp.rows_per_band[l], y1 = min(y0 + bp.rows_per_band[l], H);
+  float* gsm = bsm;                              // gout tile   [64][128]
+  float* asm_ = gsm + kNR * kC;                  // A           [64][128]  (compacted rows)
+  float* wxs = asm_ + kNR * kC;                  // wx          [64][Wp]
+  __shared__ int s_act[kNR], s_xlo[kNR], s_xhi[kNR], s_nact, s_g0, s_g1;
+  if (tid == 0) {                                // groups of frame n: contiguous in the bucket order
+    const int G = p.hdr[0];
+    int a = 0, b = G;
+    while (a < b) { const int m = (a + b) >> 1; if (p.grp_frame[m] < n) a = m + 1; else b = m; }
+    int e = a;
+    while (e < G && p.grp_frame[e] == n) ++e;
+    s_g0 = a; s_g1 = e;
+  }
+  __syncthreads();
+  const int g0 = s_g0, g1 = s_g1;
+  float* out = bp.gfeat[l] + ((long long)n * C + c0) * H * W;
+  const int nxc = (W + 31) / 32, ncg = (cn + kBwdCT - 1) / kBwdCT;   // tasks per row: x chunks x channel groups
+  for (int y = y0; y < y1; ++y) {
+    // accumulators live across the frame's groups: a task's 8 sums per thread; tasks are walked twice per group pass,
+    // so they are kept in shared-memory-free registers only when there is one group; the general case re-adds from global
+    for (int g = g0; g < max(g1, g0 + 1); ++g) {
+      const bool have = g < g1;
+      const int nroi = have ? p.grp_count[g] : 0, start = have ? p.grp_start[g] : 0;
+      const float* tab = p.wtab + (long long)g * p.wtab_stride;
+      __syncthreads();
+      if (have && (y == y0 || g1 - g0 > 1)) {      // tiles of this group (once per band when the frame has a single group)
+        for (int i = tid; i < kNR * kC; i += kBwdThreads) {
+          const int r = i / kC, c = i % kC;
+          gsm[i] = (r < nroi && c < cn) ? __ldg(bp.gout + (long long)__ldg(p.perm + start + r) * 4 * C + (long long)l * C + c0 + c) : 0.f;
+        }
+        for (int i = tid; i < kNR * Wp; i += kBwdThreads) wxs[i] = __ldg(tab + lv.wx_off + i);
+        __syncthreads();
+        if (tid < kNR) {                         // x window of every ROI slot: tasks skip the ROIs that miss their 32 columns
+          int lo = W, hi = -1;
+          if (tid < nroi)
+            for (int x = 0; x < W; ++x) if (wxs[tid * Wp + x] != 0.f) { lo = min(lo, x); hi = x; }
+          s_xlo[tid] = lo; s_xhi[tid] = hi;
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {                           // ROIs with weight on this row, compacted in ascending slot order (ballots)
+        const bool f0 = lane < nroi && __ldg(tab + lv.wy_off + y * kNR + lane) != 0.f;
+        const bool f1 = lane + 32 < nroi && __ldg(tab + lv.wy_off + y * kNR + lane + 32) != 0.f;
+        const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1), lt = (1u << lane) - 1u;
+        if (f0) s_act[__popc(m0 & lt)] = lane;
+        if (f1) s_act[__popc(m0) + __popc(m1 & lt)] = lane + 32;
+        if (lane == 0) s_nact = __popc(m0) + __popc(m1);
+      }
+      __syncthreads();
+      const int nact = s_nact;
+      for (int i = tid; i < nact * kC; i += kBwdThreads) {
+        const int a = i / kC, c = i % kC, r = s_act[a];
+        asm_[a * kC + c] = __fmul_rn(gsm[r * kC + c], __ldg(tab + lv.wy_off + y * kNR + r));
+      }
+      __syncthreads();
+      for (int task = warp; task < nxc * ncg; task += kBwdThreads / 32) {
+        const int xc = task % nxc, cg = task / nxc;
+        const int x = xc * 32 + lane;
+        float acc[kBwdCT];
+#pragma unroll
+        for (int k = 0; k < kBwdCT; ++k) acc[k] = 0.f;
+        if (x < W) {
+          for (int a = 0; a < nact; ++a) {
+            const int r = s_act[a];
+            if (xc * 32 > s_xhi[r] || xc * 32 + 31 < s_xlo[r]) continue;      // warp-uniform: this ROI has no weight in these columns
+            const float w = wxs[r * Wp + x];
+            const float4 a0 = *reinterpret_cast<const float4*>(asm_ + a * kC + cg * kBwdCT);
+            const float4 a1 = *reinterpret_cast<const float4*>(asm_ + a * kC + cg * kBwdCT + 4);
+            acc[0] = fmaf(a0.x, w, acc[0]); acc[1] = fmaf(a0.y, w, acc[1]); acc[2] = fmaf(a0.z, w, acc[2]); acc[3] = fmaf(a0.w, w, acc[3]);
+            acc[4] = fmaf(a1.x, w, acc[4]); acc[5] = fmaf(a1.y, w, acc[5]); acc[6] = fmaf(a1.z, w, acc[6]); acc[7] = fmaf(a1.w, w, acc[7]);
+          }
+#pragma unroll
+          for (int k = 0; k < kBwdCT; ++k) {
+            const int c = cg * kBwdCT + k;
+            if (c < cn) {
+              float* dst = out + ((long long)c * H + y) * W + x;
+              *dst = g == g0 ? acc[k] : __fadd_rn(*dst, acc[k]);   // frames with > 64 ROIs: groups added in bucket order
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+struct BwdPlan {
+  BwdParams bp;
+  size_t off_hdr, off_grp, off_perm, off_pair, off_wtab, total, weights_smem, smem;
+  int bands_total;
+};
+
+bool make_bwd_plan(const int Hl[4], const int Wl[4], int N, int C, int R, BwdPlan& pl) {
+  TcPool& kp = pl.bp.tp;
+  if (N < 1 || N > kMaxFrames || N > 65535 || R < 1 || C < 1 || (C + kC - 1) / kC > 65535) return false;
+  int wy_off = 0, wmax = 0;
+  pl.weights_smem = 0;
+  for (int l = 0; l < 4; ++l) {
+    LevelInfo& lv = kp.lv[l];
+    lv = LevelInfo();
+    lv.H = Hl[l]; lv.W = Wl[l]; lv.Wp = (Wl[l] + 3) / 4 * 4;
+    lv.mode = MODE_NONE;
+    if ((size_t)kNR * (Hl[l] + Wl[l]) * 4 > 160 * 1024 || lv.Wp > 512) return false;
+    pl.weights_smem = std::max(pl.weights_smem, (size_t)kNR * (Hl[l] + Wl[l]) * 4);
+    wmax = std::max(wmax, lv.Wp);
+    lv.wy_off = wy_off; wy_off += Hl[l] * kNR;
+  }
+  int wx_off = wy_off;
+  for (int l = 0; l < 4; ++l) { kp.lv[l].wx_off = wx_off; wx_off += kNR * kp.lv[l].Wp; }
+  kp.wtab_stride = (wx_off + 3) / 4 * 4;
+  kp.btab_stride = 0; kp.items_per_group = 0;
+  kp.N = N; kp.R = R; kp.C = C; kp.tables_only = 1;
+  kp.Gb = std::min(N, R) + R / kNR;
+  pl.smem = ((size_t)2 * kNR * kC + (size_t)kNR * wmax) * sizeof(float);
+  // bands: ~8 CTAs per SM over all frames; at least 2 rows per band
+  long long rows_total = 0;
+  for (int l = 0; l < 4; ++l) rows_total += Hl[l];
+  const long long cchunks = (C + kC - 1) / kC;
+  long long rpb = std::max<long long>(2, rows_total * N * cchunks / (kNumSMs * 8));
+  int b0 = 0;
+  for (int l = 0; l < 4; ++l) {
+    pl.bp.rows_per_band[l] = (int)std::min<long long>(rpb, Hl[l]);
+    pl.bp.nband[l] = (Hl[l] + pl.bp.rows_per_band[l] - 1) / pl.bp.rows_per_band[l];
+    pl.bp.band0[l] = b0; b0 += pl.bp.nband[l];
+  }
+  pl.bands_total = b0;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+  pl.off_hdr = take(64);
+  pl.off_grp = take((size_t)kp.Gb * 3 * sizeof(int));
+  pl.off_perm = take((size_t)R * sizeof(int));
+  pl.off_pair = take((size_t)kp.Gb * 4 * sizeof(int));
+  pl.off_wtab = take((size_t)kp.Gb * kp.wtab_stride * sizeof(float));
+  pl.total = o;
+  return pl.total <= ((size_t)2 << 30);
+}
+
+}  // namespace
+
+size_t roi_pool_bwd_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R) {
+  BwdPlan pl;
+  return make_bwd_plan(Hl, Wl, N, C, R, pl) ? pl.total : 0;
+}
+
+// Deterministic backward.  Returns DMM_OK when launched (g_feat is then fully overwritten), -1 when the shapes are outside
+// its envelope (the caller falls back to the atomic scatter kernel, which needs zero-initialised g_feat), or DMM_ERR_*.
+int roi_pool_bwd_try_launch(const float* g_out, const int Hl[4], const int Wl[4], int N, int C, const float* rois, int R,
+                            float* const g_feat[4], void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  BwdPlan pl;
+  if (!workspace || ((uintptr_t)workspace & 255u) || !make_bwd_plan(Hl, Wl, N, C, R, pl) || workspace_bytes < pl.total) return -1;
+  TcPool& kp = pl.bp.tp;
+  uint8_t* ws = (uint8_t*)workspace;
+  kp.rois = rois; kp.out = nullptr;
+  kp.hdr = (int*)(ws + pl.off_hdr);
+  kp.grp_frame = (int*)(ws + pl.off_grp);
+  kp.grp_start = kp.grp_frame + kp.Gb;
+  kp.grp_count = kp.grp_start + kp.Gb;
+  kp.perm = (int*)(ws + pl.off_perm);
+  kp.pair_ctr = (int*)(ws + pl.off_pair);
+  kp.ranges = nullptr; kp.btab = nullptr; kp.partial = nullptr; kp.trace = nullptr;
+  kp.wtab = (float*)(ws + pl.off_wtab);
+  pl.bp.gout = g_out;
+  for (int l = 0; l < 4; ++l) pl.bp.gfeat[l] = g_feat[l];
+  static size_t attr_w[64] = {0}, attr_b[64] = {0};
+  int dev = 0;
+  DMM_CUDA_TRY(cudaGetDevice(&dev));
+  const int di = dev & 63;
+  tc_group_kernel<<<1, 1024, 0, st>>>(kp);
+  if (pl.weights_smem > 48 * 1024 && attr_w[di] < pl.weights_smem) {
+    DMM_CUDA_TRY(cudaFuncSetAttribute(tc_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.weights_smem));
+    attr_w[di] = pl.weights_smem;
+  }
+  tc_weights_kernel<<<dim3(kp.Gb, 4), 256, pl.weights_smem, st>>>(kp);
+  if (pl.smem > 48 * 1024 && attr_b[di] < pl.smem) {
+    DMM_CUDA_TRY(cudaFuncSetAttribute(roi_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    attr_b[di] = pl.smem;
+  }
+  roi_pool_bwd_kernel<<<dim3(pl.bands_total, N, (C + kC - 1) / kC), kBwdThreads, pl.smem, st>>>(pl.bp);
+  return check_launch();
+}
+
+namespace {
 }  // namespace
 
 size_t roi_pool_tc_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R) {

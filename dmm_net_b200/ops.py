@@ -213,7 +213,8 @@ def mask_iou_pairwise(prop: torch.Tensor, tmpl: torch.Tensor, tmpl2: Optional[to
     out = {"iou": iou, "iou2": iou2, "sim": sim, "counts": counts}
     if B == 0 or P == 0 or O == 0:
         return out
-    if tmpl2 is not None and (P + 2 * O > 64 or 2 * O > 16) and P + O <= 64 and O <= 16:
+    one_pass_wide = ragged is None and HW % 4 == 0 and P <= 64 and 2 * O <= 32 and P + 2 * O <= 96    # K1's 96-row TMA tile
+    if tmpl2 is not None and not one_pass_wide and (P + 2 * O > 64 or 2 * O > 16) and P + O <= 64 and O <= 16:
         # both template sets in one pass would need several tiles (rows re-read, LDG path); two single-tile passes
         # keep the TMA ring and read the proposals twice instead of up to four times
         first = mask_iou_pairwise(ragged if ragged is not None else prop, tmpl, None, n_prop, n_tmpl, cos, w_cos, w_iou,
@@ -614,17 +615,27 @@ class _RoiPoolFn(torch.autograd.Function):
         N, C = shapes[0][:2]
         R = rois.shape[0]
         g_out = g_out.contiguous().float()
-        gf = [torch.zeros(s, device=rois.device) for s in shapes]
         Hl = (ctypes.c_int * 4)(*[s[2] for s in shapes])
         Wl = (ctypes.c_int * 4)(*[s[3] for s in shapes])
+        # deterministic gather (overwrites every element: plain empty buffers) when the library has a plan for these
+        # shapes, else the atomic scatter into zeroed buffers
+        ws_bytes = lib.dmm_roi_mean_pool_bwd_workspace_bytes(Hl, Wl, N, C, R) if (R * C > 0 and ROI_POOL_BWD_IMPL != "atomic") else 0
+        gf = [(torch.empty if ws_bytes else torch.zeros)(s, device=rois.device) for s in shapes]
         ptrs = (ctypes.c_void_p * 4)(*[g.data_ptr() for g in gf])
         if R * C > 0:
-            rc = lib.dmm_roi_mean_pool_bwd(_p(g_out), Hl, Wl, N, C, _p(rois), R, ptrs, _stream())
+            ws = torch.empty(ws_bytes, device=rois.device, dtype=torch.uint8) if ws_bytes else None
+            wrote = ctypes.c_int(0)
+            rc = lib.dmm_roi_mean_pool_bwd(_p(g_out), Hl, Wl, N, C, _p(rois), R, ptrs, _p(ws), ws_bytes, 2 if ws_bytes else 1,
+                                           ctypes.byref(wrote), _stream())
             _lib.check(rc, "dmm_roi_mean_pool_bwd")
+        else:
+            for g in gf:
+                g.zero_()
         return (None, None, *gf)
 
 
 ROI_POOL_IMPLS = {"auto": 0, "simt": 1, "tc": 2}
+ROI_POOL_BWD_IMPL = "auto"          # "atomic" forces the legacy scatter kernel (tests compare the two)
 
 
 @_op("K5 roi_mean_pool")

@@ -124,7 +124,7 @@ def clip_eval(clips, frames, proposals=50, objects=5, size=(256, 448), lazy=Fals
                 out, tplt, _, mask_last = model.inference(infos, props, fb, mask_last, tplt)
             levels = ops.mask_pyramid(prev, mask0, out, 4)           # K6: decoder inputs of every object (identity decoder here)
             labels = ops.merge_labels(out.view(B, F, -1), n_obj)     # K7: merged label map (evaluator.py:139-145)
-            checks.append((out, levels[-1], labels))
+            checks = checks[-1:] + [(out, levels[-1], labels)]   # keep two frames alive, not the clip: a steady allocation pattern
         t1.record()
     ops.set_kernel_timer(None)
     torch.cuda.synchronize()

@@ -193,9 +193,14 @@ size_t dmm_roi_mean_pool_workspace_bytes(const int Hl[4], const int Wl[4], int N
 int dmm_roi_mean_pool(const float* const feat[4], const int Hl[4], const int Wl[4], int N, int C,
                       const float* rois, int R, float* out, void* workspace, size_t workspace_bytes, int impl,
                       void* stream);
-/* g_feat[l] [N][C][Hl][Wl] must be zero-initialised by the caller; gradients are accumulated with atomics. */
+/* Backward.  Two implementations: a deterministic GATHER (per frame, level, row: sum over the frame's ROIs in bucket
+ * order; every gradient element written once, no atomics; needs `workspace`, dmm_roi_mean_pool_bwd_workspace_bytes) that
+ * OVERWRITES g_feat, and the atomic scatter (any shape) that ACCUMULATES into a zero-initialised g_feat.
+ * impl: 0 auto, 1 scatter only, 2 gather required.  *wrote_all (may be NULL) = 1 when g_feat was fully overwritten. */
+size_t dmm_roi_mean_pool_bwd_workspace_bytes(const int Hl[4], const int Wl[4], int N, int C, int R);
 int dmm_roi_mean_pool_bwd(const float* g_out, const int Hl[4], const int Wl[4], int N, int C, const float* rois,
-                          int R, float* const g_feat[4], void* stream);
+                          int R, float* const g_feat[4], void* workspace, size_t workspace_bytes, int impl,
+                          int* wrote_all, void* stream);
 
 /* ---- K6: decoder mask-input pyramid -------------------------------------------------
  * Replaces, for every object at once, trainer.py:256-263 / evaluator.py:187-194:

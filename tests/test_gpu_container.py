@@ -42,10 +42,46 @@ def test_roi_mean_pool_forward_and_backward():
     assert got.shape == (rois.shape[0], 4 * C)
     np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=0, atol=1e-5)
     w = torch.randn(want.shape, generator=gen)
-    (want * w).sum().backward()
+    # reference gradient in float64: the stand-in's own fp32 backward adds up to 784 equal terms sequentially for the point
+    # ROI (2e-5 off); the gather kernel multiplies the two 1-D weights instead
+    want64_in = [f.double().requires_grad_(True) for f in feats]
+    (orc.roi_mean_pool(want64_in, rois.double()) * w.double()).sum().backward()
     (got * w.to(DEV)).sum().backward()
-    for a, b in zip(got_in, want_in):
-        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-4, atol=1e-5)   # fp32 atomics order
+    for a, b in zip(got_in, want64_in):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.float().numpy(), rtol=1e-5, atol=2e-6)   # deterministic gather
+
+
+@pytest.mark.parametrize("N,C,H,W,counts", [(3, 128, 256, 448, [50, 0, 9]), (2, 40, 128, 192, [130, 3]), (2, 136, 64, 96, [5, 70])])
+def test_roi_mean_pool_backward_is_a_deterministic_gather(N, C, H, W, counts):
+    """K5 backward: every gradient element written once in a fixed order -- bit-identical run to run, equal (to fp32
+    summation order) to the atomic scatter and to autograd through the ROIAlign stand-in; frames with several ROI
+    groups (> 64 ROIs), a frame without ROIs (gradient exactly zero), any channel count."""
+    gen = torch.Generator().manual_seed(7 * N + C)
+    feats, rois = _tc_case(gen, N, H, W, counts, C=C)
+    rois = rois[(rois[:, 0] >= 0) & (rois[:, 0] < N)]
+    w = torch.randn(rois.shape[0], 4 * C, generator=gen)
+
+    def grads(mode):
+        ops.ROI_POOL_BWD_IMPL = mode
+        try:
+            fin = [f.to(DEV).requires_grad_(True) for f in feats]
+            out = ops.roi_mean_pool(fin, rois.to(DEV))
+            (out * w.to(DEV)).sum().backward()
+            return [f.grad for f in fin]
+        finally:
+            ops.ROI_POOL_BWD_IMPL = "auto"
+
+    a, b, c = grads("auto"), grads("auto"), grads("atomic")
+    want_in = [f.double().requires_grad_(True) for f in feats]                        # float64 reference (see the test above)
+    (orc.roi_mean_pool(want_in, rois.double()) * w.double()).sum().backward()
+    for l in range(4):
+        assert torch.equal(a[l], b[l]), l                                             # run to run
+        scale = max(1.0, float(want_in[l].grad.abs().max()))
+        np.testing.assert_allclose(a[l].cpu().numpy(), c[l].cpu().numpy(), rtol=0, atol=2e-5 * scale)   # atomics: order-dependent
+        np.testing.assert_allclose(a[l].cpu().numpy(), want_in[l].grad.float().numpy(), rtol=0, atol=3e-6 * scale)
+        empty = [n for n, cnt in enumerate(counts) if cnt == 0 and not ((rois[:, 0] == n).any())]
+        for n in empty:
+            assert float(a[l][n].abs().sum()) == 0.0
 
 
 def _tc_case(gen, N, H, W, counts, C=128):
