@@ -192,11 +192,38 @@ __global__ void __launch_bounds__(1024) tc_group_kernel(const TcPool p) {
   }
   if (tid == 1023) { p.hdr[0] = warp_g[31]; p.hdr[1] = 0; }
   __syncthreads();
-  for (int i = tid; i < p.N; i += 1024) cnt[i] = 0;          // reuse as cursors
+  // perm: the ROIs of a frame in INPUT ORDER (stable) -- the slot of a ROI inside its group fixes the order in which the
+  // backward gather adds its contribution, so it must not depend on the arrival order of atomics.
+  // Fast path: rows already grouped by ascending frame id with no invalid row (what convert_to_roi_format produces).
+  __shared__ int s_unsorted;
+  if (tid == 0) s_unsorted = 0;
   __syncthreads();
   for (int i = tid; i < p.R; i += 1024) {
     const int n = (int)p.rois[(long long)i * 5];
-    if (n >= 0 && n < p.N) p.perm[roi0[n] + atomicAdd(&cnt[n], 1)] = i;   // order inside a frame is irrelevant to the results
+    const int prev = i ? (int)p.rois[(long long)(i - 1) * 5] : 0;
+    if (n < 0 || n >= p.N || n < prev) s_unsorted = 1;
+  }
+  for (int i = tid; i < p.N; i += 1024) cnt[i] = 0;          // reuse as cursors
+  __syncthreads();
+  if (!s_unsorted) {
+    for (int i = tid; i < p.R; i += 1024) p.perm[i] = i;
+    return;
+  }
+  // general path: stable counting sort, 1024 rows at a time; inside a warp the rows of one frame are ranked with
+  // match.any, the 32 warps then take turns on the per-frame cursors
+  for (int c0 = 0; c0 < p.R; c0 += 1024) {
+    const int i = c0 + tid;
+    const int n = i < p.R ? (int)p.rois[(long long)i * 5] : -1;
+    const bool ok = n >= 0 && n < p.N;
+    const unsigned peers = __match_any_sync(0xffffffffu, ok ? n : -1 - lane);
+    const int rank = __popc(peers & ((1u << lane) - 1u)), leader = __ffs(peers) - 1;
+    int base = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (warp == w && ok && lane == leader) { base = cnt[n]; cnt[n] = base + __popc(peers); }
+      __syncthreads();
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ok) p.perm[roi0[n] + base + rank] = i;
   }
 }
 
@@ -790,7 +817,7 @@ bool make_plan(const int Hl[4], const int Wl[4], int N, int C, int R, Plan& pl) 
 // non-zero are compacted and A[r][c] = gout[r][c] * wy[r][y] staged once; lanes run along x (coalesced stores), each
 // thread carries 8 channels: 8 FMAs per (wx load + two broadcast LDS.128).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;
 constexpr int kBwdCT = 8;                       // channels per thread
 
 struct BwdParams {
@@ -816,7 +843,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_pool_bwd_kernel(const BwdPara
   float* gsm = bsm;                              // gout tile   [64][128]
   float* asm_ = gsm + kNR * kC;                  // A           [64][128]  (compacted rows)
   float* wxs = asm_ + kNR * kC;                  // wx          [64][Wp]
-  __shared__ int s_act[kNR], s_xlo[kNR], s_xhi[kNR], s_nact, s_g0, s_g1;
+  __shared__ int s_act[kNR], s_nact, s_g0, s_g1;
   if (tid == 0) {                                // groups of frame n: contiguous in the bucket order
     const int G = p.hdr[0];
     int a = 0, b = G;
@@ -843,13 +870,6 @@ __global__ void __launch_bounds__(kBwdThreads) roi_pool_bwd_kernel(const BwdPara
           gsm[i] = (r < nroi && c < cn) ? __ldg(bp.gout + (long long)__ldg(p.perm + start + r) * 4 * C + (long long)l * C + c0 + c) : 0.f;
         }
         for (int i = tid; i < kNR * Wp; i += kBwdThreads) wxs[i] = __ldg(tab + lv.wx_off + i);
-        __syncthreads();
-        if (tid < kNR) {                         // x window of every ROI slot: tasks skip the ROIs that miss their 32 columns
-          int lo = W, hi = -1;
-          if (tid < nroi)
-            for (int x = 0; x < W; ++x) if (wxs[tid * Wp + x] != 0.f) { lo = min(lo, x); hi = x; }
-          s_xlo[tid] = lo; s_xhi[tid] = hi;
-        }
       }
       __syncthreads();
       if (warp == 0) {                           // ROIs with weight on this row, compacted in ascending slot order (ballots)
@@ -875,9 +895,7 @@ __global__ void __launch_bounds__(kBwdThreads) roi_pool_bwd_kernel(const BwdPara
         for (int k = 0; k < kBwdCT; ++k) acc[k] = 0.f;
         if (x < W) {
           for (int a = 0; a < nact; ++a) {
-            const int r = s_act[a];
-            if (xc * 32 > s_xhi[r] || xc * 32 + 31 < s_xlo[r]) continue;      // warp-uniform: this ROI has no weight in these columns
-            const float w = wxs[r * Wp + x];
+            const float w = wxs[s_act[a] * Wp + x];
             const float4 a0 = *reinterpret_cast<const float4*>(asm_ + a * kC + cg * kBwdCT);
             const float4 a1 = *reinterpret_cast<const float4*>(asm_ + a * kC + cg * kBwdCT + 4);
             acc[0] = fmaf(a0.x, w, acc[0]); acc[1] = fmaf(a0.y, w, acc[1]); acc[2] = fmaf(a0.z, w, acc[2]); acc[3] = fmaf(a0.w, w, acc[3]);
