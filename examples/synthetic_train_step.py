@@ -33,6 +33,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from backbone import Encoder                                        # noqa: E402
 from dmm_net_b200 import ops                                         # noqa: E402
 from dmm_net_b200.modules.dmm_model import DMM_Model                # noqa: E402
+from dmm_net_b200.sharding import FlatGradBucket                   # noqa: E402
 from dmm_net_b200.synth import default_cfg                          # noqa: E402
 from dmm_net_b200.utils.boxlist import BoxList                      # noqa: E402
 from dmm_net_b200.utils.masker import Masker                        # noqa: E402
@@ -69,41 +70,6 @@ def synth_batch(gen, B, Fo, H, W, P, dev):
     prop = torch.cat([torch.minimum(prop[..., :2], prop[..., 2:] - 2), prop[..., 2:]], -1).clamp(min=0)
     m28 = torch.sigmoid(4 * torch.randn(B, P, 1, 28, 28, generator=gen, device=dev) + 2)
     return img, gt, prop, m28
-
-
-class FlatGradBucket:
-    """ONE gradient bucket for the whole model: every parameter's ``.grad`` is a view into one flat fp32 buffer, so the
-    data-parallel exchange of a step is a single NCCL all-reduce over NVLink with no per-parameter hooks, no bucket
-    copies and no per-parameter messages (the reference sends one message per parameter tensor, train.py:62-68, on top
-    of DDP's buckets, train.py:178-184).  Autograd accumulates into the views in place."""
-
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-
-    def zero(self):
-        self.flat.zero_()
-
-    def all_reduce_mean(self):
-        import torch.distributed as dist
-        dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
-
-    def rendezvous(self):
-        """4-byte all-reduce: returns (on the stream) once every rank has finished its backward -- separates the wait for the
-        slowest rank from the time of the gradient exchange itself"""
-        import torch.distributed as dist
-        if not hasattr(self, "_probe"):
-            self._probe = torch.zeros(1, device=self.flat.device)
-        dist.all_reduce(self._probe)
-
-    @property
-    def nbytes(self):
-        return self.flat.numel() * 4
 
 
 def train_loop(arch="resnet50", clips=4, frames=3, objects=3, proposals=50, size=(256, 448), steps=5, warmup=1,

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dmm_net_b200.sharding import aggregate_throughput, max_over_ranks, shard_indices
+from dmm_net_b200.sharding import FlatGradBucket, aggregate_throughput, max_over_ranks, shard_indices
 
 
 def _free_port():
@@ -50,3 +50,36 @@ def test_single_process_identity():
     assert shard_indices(5, 0, 1) == [0, 1, 2, 3, 4]
     assert max_over_ranks(3.5) == 3.5
     assert aggregate_throughput(10, 100.0) == 100.0
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                           # same weights on both ranks
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    bucket = FlatGradBucket(net.parameters())
+    views = [p.grad.data_ptr() for p in net.parameters()]
+    x = torch.full((4, 6), float(rank + 1))                       # different data per rank
+    for _ in range(2):                                             # second step: grads still live in the bucket
+        bucket.zero()
+        net(x).pow(2).sum().backward()
+        local = bucket.flat.clone()
+        bucket.rendezvous()
+        bucket.all_reduce_mean()
+    assert [p.grad.data_ptr() for p in net.parameters()] == views  # autograd accumulated in place: still the views
+    torch.save({"local": local, "mean": bucket.flat.clone(), "nbytes": bucket.nbytes}, os.path.join(out_dir, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_all_reduce(tmp_path):
+    """The training step's only collective (examples/synthetic_train_step.py, bench.py train leg): every gradient is a
+    view into one flat buffer, one all-reduce averages them over the ranks."""
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"g{r}.pt")) for r in range(world)]
+    want = (res[0]["local"] + res[1]["local"]) / 2
+    assert not torch.equal(res[0]["local"], res[1]["local"])
+    for r in res:
+        assert torch.allclose(r["mean"], want, rtol=0, atol=1e-7)
+        assert r["nbytes"] == 4 * (6 * 5 + 5 + 5 * 3 + 3)
