@@ -62,6 +62,7 @@ SIGNATURES = {
     "dmm_paste_masks_workspace_bytes": (_sz, [_i]),
     "dmm_paste_masks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dmm_paste_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp]),
+    "dmm_paste_apply_bwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "dmm_box_nms": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
 }
 

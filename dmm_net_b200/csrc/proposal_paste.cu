@@ -441,6 +441,101 @@ extern "C" int dmm_paste_apply(const float* Bmat, const float* masks, const floa
   return check_launch();
 }
 
+// ---- K10 backward: gradient w.r.t. the assignment coefficients ---------------------------------------------------------
+// out[b, row(o)] = sum_p Bm[b,o,p] * paste(det src[b,p])  =>  g_Bm[b,o,p] = < g_out[b, row(o)], paste(det src[b,p]) >  over the
+// detection's (clipped) box, for the entries the solver selected (sel[b,o,p] != 0: Bm = R * logic, match_model.py:128-130).
+// The mask-head outputs themselves carry no gradient in the reference (proposals are loaded offline,
+// dmm/modules/model_encoder.py), so this is the whole backward of the lazy pipeline: training no longer has to
+// materialise the P pasted masks.  One CTA per (problem, template row); for every selected detection the padded 28x28
+// mask sits in shared memory, threads walk the box with the forward's taps, a fixed-order block reduction gives the dot
+// product: deterministic.
+struct PasteApplyBwdParams {
+  const float* gout;     // [B][O_out][im_h][im_w] (batch stride gout_bs)
+  const float* sel;      // [B][O][MS]  selection mask (non-zero: gradient flows)
+  const float* masks;    // [Nsrc][M][M]
+  const float* boxes;    // [Nsrc][4]
+  const int* src;        // [B][P]
+  const int* n_prop;
+  const int* n_tmpl;
+  const int* row_map;    // [B][O] or NULL
+  float* g_coef;         // [B][O][MS]
+  long long gout_bs;
+  int B, P, O, MS, O_out, M, pad, im_h, im_w;
+  float scale;
+};
+
+__global__ void __launch_bounds__(kThreads) paste_apply_bwd_kernel(const PasteApplyBwdParams p) {
+  __shared__ float sm[kMaxMp * kMaxMp];
+  __shared__ float s_red[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / p.O, o = blockIdx.x % p.O;
+  const int Mp = p.M + 2 * p.pad;
+  const int np = p.n_prop ? clampi(p.n_prop[b], 0, p.P) : p.P;
+  const int nt = p.n_tmpl ? clampi(p.n_tmpl[b], 0, p.O) : p.O;
+  float* grow = p.g_coef + ((long long)b * p.O + o) * p.MS;
+  for (int c = tid; c < p.MS; c += kThreads) grow[c] = 0.f;
+  const int f = o < nt ? (p.row_map ? p.row_map[(long long)b * p.O + o] : o) : -1;
+  if (f < 0 || f >= p.O_out) return;                               // row not written by the forward: no gradient
+  const float* g = p.gout + (long long)b * p.gout_bs + (long long)f * p.im_h * p.im_w;
+  const float* srow = p.sel + ((long long)b * p.O + o) * p.MS;
+  for (int c = 0; c < np; ++c) {                                   // block-uniform loop over the selected detections
+    const int det = p.src[(long long)b * p.P + c];
+    if (srow[c] == 0.f || det < 0) continue;
+    __syncthreads();                                               // previous detection's tile / partials consumed
+    const float* src = p.masks + (long long)det * p.M * p.M;
+    for (int i = tid; i < Mp * Mp; i += kThreads) {
+      const int y = i / Mp - p.pad, x = i % Mp - p.pad;
+      sm[i] = (y >= 0 && y < p.M && x >= 0 && x < p.M) ? src[y * p.M + x] : 0.f;
+    }
+    const BoxI bx = expand_box(p.boxes + 4LL * det, p.scale);
+    const int x0c = max(bx.x0, 0), x1c = min(bx.x1 + 1, p.im_w);
+    const int y0c = max(bx.y0, 0), y1c = min(bx.y1 + 1, p.im_h);
+    __syncthreads();
+    float acc = 0.f;
+    const int bw = x1c - x0c, bh = y1c - y0c;
+    if (bw > 0 && bh > 0) {
+      const float sc_y = (float)Mp / (float)bx.h, sc_x = (float)Mp / (float)bx.w;
+      for (int it = tid; it < bw * bh; it += kThreads) {
+        const int Y = y0c + it / bw, X = x0c + it % bw;
+        const Tap ty = tap(Y - bx.y0, sc_y, Mp), tx = tap(X - bx.x0, sc_x, Mp);
+        const float* r0 = sm + ty.i0 * Mp;
+        const float* r1 = sm + ty.i1 * Mp;
+        const float top = fmaf(tx.l0, r0[tx.i0], __fmul_rn(tx.l1, r0[tx.i1]));
+        const float bot = fmaf(tx.l0, r1[tx.i0], __fmul_rn(tx.l1, r1[tx.i1]));
+        const float m = fmaf(ty.l0, top, __fmul_rn(ty.l1, bot));
+        acc = fmaf(g[(long long)Y * p.im_w + X], m, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) t = __fadd_rn(t, s_red[w]);
+      grow[c] = t;
+    }
+  }
+}
+
+extern "C" int dmm_paste_apply_bwd(const float* g_out, long long gout_bstride, const float* sel, const float* masks,
+                                   const float* boxes, const int* src_index, int B, int P, int O, int MS, int M, int padding,
+                                   int im_h, int im_w, const int* n_prop, const int* n_tmpl, const int* row_map, int O_out,
+                                   float* g_Bmat, void* stream) {
+  if (B < 0 || P < 0 || O < 0 || MS < P || M <= 0 || padding < 1 || im_h < 0 || im_w < 0 || O_out < 0) return DMM_ERR_INVALID_ARGUMENT;
+  if (M + 2 * padding > kMaxMp || P > 128) return DMM_ERR_UNSUPPORTED_SHAPE;
+  if (B == 0 || O == 0) return DMM_OK;
+  if (!g_Bmat || (P > 0 && im_h * im_w > 0 && (!g_out || !sel || !masks || !boxes || !src_index))) return DMM_ERR_INVALID_ARGUMENT;
+  PasteApplyBwdParams kp;
+  kp.gout = g_out; kp.gout_bs = gout_bstride; kp.sel = sel; kp.masks = masks; kp.boxes = boxes; kp.src = src_index;
+  kp.n_prop = n_prop; kp.n_tmpl = n_tmpl; kp.row_map = row_map; kp.g_coef = g_Bmat;
+  kp.B = B; kp.P = P; kp.O = O; kp.MS = MS; kp.O_out = O_out; kp.M = M; kp.pad = padding; kp.im_h = im_h; kp.im_w = im_w;
+  kp.scale = (float)((double)(M + 2 * padding) / (double)M);
+  cudaStream_t st = (cudaStream_t)stream;
+  paste_apply_bwd_kernel<<<(unsigned)((long long)B * O), kThreads, 0, st>>>(kp);
+  return check_launch();
+}
+
 extern "C" int dmm_box_nms(const float* boxes, const float* scores, const int* n_boxes, int F, int n_max, float thresh,
                            int max_keep, long long* keep, int* n_keep, void* stream) {
   if (F < 0 || n_max < 0) return DMM_ERR_INVALID_ARGUMENT;

@@ -149,6 +149,29 @@ class DMM_Model(nn.Module):
         detections: list (one per video) of BoxList-likes with ``bbox`` [n,4] (detector boxes), field ``mask`` [n,1,M,M]
         (mask-head probabilities, NOT pasted) and ``scores`` / ``objectness`` [n].
         Returns (output_mask [B,F,H,W], tplt_dict, [], out_mask_last, keep) -- ``keep`` = (index table [B,P], n_prop [B])."""
+        extra = infos.get('extra_frame')
+        skip = torch.as_tensor(extra).bool().view(-1) if extra is not None else None
+        with torch.no_grad():
+            output_mask, out_mask_last, _, keep = self._lazy(detections, backbone_feature, mask_last_occurence, tplt_dict,
+                                                            infos['valid'], None, skip, nms_thresh, max_proposals, mask_threshold,
+                                                            padding)
+        return output_mask, tplt_dict, [], out_mask_last, keep
+
+    def forward_lazy(self, args, detections, backbone_feature, mask_last_occurence, tplt_dict, tplt_valid_batch, targets,
+                     nms_thresh=0.8, max_proposals=50, mask_threshold=0.5, padding=1):
+        """``forward`` (training: match loss + gradients) through the lazy pipeline: the P pasted proposal masks of
+        masker.py:181-206 are never materialised in training either.  Gradients flow through K10's backward into the
+        assignment, through the solver and the cosine into the pooled features and the backbone maps; the detections'
+        mask-head outputs are constants (offline proposals in the reference).
+        Returns (output_mask [B,F,H,W], tplt_dict, match_loss list, out_mask_last, keep)."""
+        assert (targets is not None)
+        output_mask, out_mask_last, cost_loss, keep = self._lazy(detections, backbone_feature, mask_last_occurence, tplt_dict,
+                                                                 tplt_valid_batch, targets, None, nms_thresh, max_proposals,
+                                                                 mask_threshold, padding)
+        return output_mask, tplt_dict, list(cost_loss.unbind(0)), out_mask_last, keep
+
+    def _lazy(self, detections, backbone_feature, mask_last_occurence, tplt_dict, tplt_valid_batch, targets, skip, nms_thresh,
+              max_proposals, mask_threshold, padding):
         B, F, H, W = CHECK4D(mask_last_occurence)
         CHECKEQ(len(detections), B)
         dev = mask_last_occurence.device
@@ -157,7 +180,8 @@ class DMM_Model(nn.Module):
         m_all = torch.cat([d.get_field('mask').reshape(len(d), d.get_field('mask').shape[-2], d.get_field('mask').shape[-1])
                            for d in detections], 0)
         b_all = torch.cat([d.bbox for d in detections], 0).to(dev)
-        pasted = ops.paste_masks(m_all, b_all, H, W, mask_threshold, padding, want_pasted=False, want_bits=True)   # K8
+        with torch.no_grad():
+            pasted = ops.paste_masks(m_all, b_all, H, W, mask_threshold, padding, want_pasted=False, want_bits=True)   # K8
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + c)
@@ -171,7 +195,7 @@ class DMM_Model(nn.Module):
             tight = torch.zeros(B * n_max, 4, device=dev).index_copy_(0, flat, pasted['tight'].float()).view(B, n_max, 4)
             score = torch.zeros(B * n_max, device=dev).index_copy_(0, flat, sc_all).view(B, n_max)
         cnt = torch.tensor(counts, dtype=torch.int32, device=dev)
-        keep, n_keep = ops.box_nms(tight, score, nms_thresh, max_proposals, cnt)                                     # K9
+        keep, n_keep = ops.box_nms(tight, score.detach(), nms_thresh, max_proposals, cnt)                           # K9
         P = n_max if max_proposals <= 0 else min(max_proposals, n_max)
         keep = keep[:, :P]
         n_prop = n_keep.clamp(max=P)
@@ -184,25 +208,37 @@ class DMM_Model(nn.Module):
         prop_feat = self.feature_extractor.pool_rois(backbone_feature, rois).view(B, P, -1)                          # K5
         prop_bits = pasted['bits'][gidx]                                                                             # [B,P,words]
         prop_score = torch.gather(score, 1, local) * kept
-        valid = infos['valid'].to(dev).float().view(B, -1)
+        valid = tplt_valid_batch.to(dev).float().view(B, -1)
         CHECKEQ(valid.shape[1], F)
         n_tmpl = valid.sum(1).round().to(torch.int32)
-        extra = infos.get('extra_frame')
-        if extra is not None:
-            n_tmpl = torch.where(torch.as_tensor(extra).bool().view(-1).to(dev), torch.zeros_like(n_tmpl), n_tmpl)
+        if skip is not None:
+            n_tmpl = torch.where(skip.to(dev), torch.zeros_like(n_tmpl), n_tmpl)
         tmpl_feat = self._stacked_templates(tplt_dict, B) * valid[:, None, :, None]
         ar = torch.arange(F, device=dev, dtype=torch.int32)[None, :].expand(B, -1)
         row_map = torch.where(valid > 0, ar, torch.full_like(ar, -1)).contiguous()
         layer = self.match_layer
+        w = float(layer.cfgs['score_weight'])
+        cos = ops.cosine_pairwise(tmpl_feat, prop_feat, n_prop, n_tmpl)                                              # K2
         with torch.no_grad():
-            cos = ops.cosine_pairwise(tmpl_feat, prop_feat, n_prop, n_tmpl)                                          # K2
-            w = float(layer.cfgs['score_weight'])
             tmpl_bits = ops.pack_masks(mask_last_occurence.float(), mask_dims=2)                                     # [B,F,words]
-            r = ops.mask_iou_pairwise_packed(prop_bits.contiguous(), tmpl_bits, None, n_prop, n_tmpl, cos=cos,
+            tgt_bits = None if targets is None else ops.pack_masks(targets.float(), mask_dims=2)
+        cost_loss = None
+        if targets is None:
+            r = ops.mask_iou_pairwise_packed(prop_bits.contiguous(), tmpl_bits, None, n_prop, n_tmpl, cos=cos.detach(),
                                              w_cos=1 - w, w_iou=w)                                                   # K1 packed
-            _, Bm, _, _, _, _, _ = ops.relax_solve(r['sim'], prop_score, n_prop, n_tmpl, layer.max_iter, layer.proj_iter,
+            sim = r['sim']
+        else:
+            r = ops.mask_iou_pairwise_packed(prop_bits.contiguous(), tmpl_bits, tgt_bits, n_prop, n_tmpl)            # both sets, one pass
+            sim = cos * (1 - w) + r['iou'] * w                                                                       # autograd sees cos
+            gt = ops.relax_solve(r['iou2'], None, n_prop, n_tmpl, 0, 0, 0.0, True, False, True)[0]                   # greedy one-hot
+            ok = (torch.arange(P, device=dev)[None, None, :] < n_prop[:, None, None]) & \
+                 (torch.arange(F, device=dev)[None, :, None] < n_tmpl[:, None, None])
+            cost_loss = (((cos - gt) ** 2) * ok).sum(dim=(1, 2)) / (n_prop * n_tmpl).clamp(min=1).float()
+            cost_loss = cost_loss * (n_tmpl > 0).float()
+        _, Bm, _, _, _, logic, _ = ops.relax_solve(sim, prop_score, n_prop, n_tmpl, layer.max_iter, layer.proj_iter,
                                                    layer.relax_lr, True, True, bool(layer.is_test))                  # K3
-            output_mask = ops.paste_apply(Bm, m_all, b_all, src_index, H, W, n_prop, n_tmpl, row_map, F, True, padding)   # K10
+        output_mask = ops.paste_apply(Bm, m_all, b_all, src_index, H, W, n_prop, n_tmpl, row_map, F, True, padding,
+                                      logic=logic)                                                                   # K10
         empty = (n_tmpl == 0).view(B, 1, 1, 1)
         out_mask_last = torch.where(empty, mask_last_occurence.to(output_mask.dtype), output_mask)
-        return output_mask, tplt_dict, [], out_mask_last, (src_index, n_prop)
+        return output_mask, out_mask_last, cost_loss, (src_index, n_prop)

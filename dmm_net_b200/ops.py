@@ -774,21 +774,60 @@ def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, im_h: int, im_w: int, 
     return out
 
 
+class _PasteApplyFn(torch.autograd.Function):
+    """K10 with a gradient for the assignment (the mask-head outputs are constants: offline proposals in the reference)."""
+
+    @staticmethod
+    def forward(ctx, Bm, logic, masks, boxes, src_index, n_prop, n_tmpl, row_map, dims):
+        lib = _lib.load()
+        im_h, im_w, O_out, zero_fill, padding = dims
+        B, O, MS = Bm.shape
+        P, M = src_index.shape[1], masks.shape[-1]
+        out = torch.empty(B, O_out, im_h, im_w, device=Bm.device)
+        step = max(1, 65535 // max(O_out, 1))
+        for s in range(0, B, step):
+            e = min(B, s + step)
+            sl = lambda t: None if t is None else t[s:e]
+            rc = lib.dmm_paste_apply(_p(Bm[s:e]), _p(masks), _p(boxes), _p(src_index[s:e]), e - s, P, O, MS, M, int(padding),
+                                     int(im_h), int(im_w), _p(sl(n_prop)), _p(sl(n_tmpl)), _p(sl(row_map)), O_out,
+                                     int(zero_fill), _p(out[s:e]), O_out * im_h * im_w, _stream())
+            _lib.check(rc, "dmm_paste_apply")
+        ctx.save_for_backward(Bm, logic, masks, boxes, src_index, n_prop, n_tmpl, row_map)
+        ctx.dims = dims
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        Bm, logic, masks, boxes, src_index, n_prop, n_tmpl, row_map = ctx.saved_tensors
+        im_h, im_w, O_out, zero_fill, padding = ctx.dims
+        B, O, MS = Bm.shape
+        P, M = src_index.shape[1], masks.shape[-1]
+        g_out = g_out.contiguous().float()
+        sel = logic if logic is not None else (Bm != 0).float()
+        gB = torch.empty_like(Bm)
+        if B * O > 0:
+            rc = lib.dmm_paste_apply_bwd(_p(g_out), O_out * im_h * im_w, _p(sel), _p(masks), _p(boxes), _p(src_index), B, P, O, MS, M,
+                                         int(padding), int(im_h), int(im_w), _p(n_prop), _p(n_tmpl), _p(row_map), O_out, _p(gB),
+                                         _stream())
+            _lib.check(rc, "dmm_paste_apply_bwd")
+        return gB, None, None, None, None, None, None, None, None
+
+
 @_op("K10 paste_apply")
 def paste_apply(Bm: torch.Tensor, masks: torch.Tensor, boxes: torch.Tensor, src_index: torch.Tensor, im_h: int, im_w: int,
                 n_prop=None, n_tmpl=None, row_map: Optional[torch.Tensor] = None, O_out: Optional[int] = None,
-                zero_fill: bool = True, padding: int = 1) -> torch.Tensor:
+                zero_fill: bool = True, padding: int = 1, logic: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused paste + assignment apply ("lazy paste", K10): out[b, row(o)] = sum_p Bm[b,o,p] * paste(masks[src_index[b,p]]).
 
     Bm [B,O,MS]; masks [Nsrc,1,M,M] / [Nsrc,M,M] mask-head outputs and boxes [Nsrc,4] of ALL detections; src_index [B,P]
     int32 = which detection sits behind column p of problem b (-1: none) -- the NMS keep list.  Returns [B,O_out,im_h,im_w],
     bit-identical to ``assign_apply(Bm, paste_masks(...)["pasted"] gathered by src_index)`` without ever writing or reading
-    the P pasted masks.  Inference only."""
-    lib = _lib.load()
+    the P pasted masks.  Differentiable w.r.t. ``Bm`` (``logic`` = the solver's selection mask restricts the gradient to the
+    selected entries, as in ``assign_apply``); the mask-head outputs are treated as constants."""
     Bm = _cuda_f32(Bm, "Bmat")
     masks, boxes = _cuda_f32(masks, "masks"), _cuda_f32(boxes, "boxes")
     B, O, MS = Bm.shape
-    M = masks.shape[-1]
     dev = Bm.device
     src_index = torch.as_tensor(src_index, device=dev).to(torch.int32).contiguous()
     P = src_index.shape[1]
@@ -796,17 +835,11 @@ def paste_apply(Bm: torch.Tensor, masks: torch.Tensor, boxes: torch.Tensor, src_
     if row_map is not None:
         row_map = torch.as_tensor(row_map, device=dev).to(torch.int32).contiguous()
         assert row_map.shape == (B, O)
+    if logic is not None:
+        logic = _cuda_f32(logic, "logic")
     O_out = int(O if O_out is None else O_out)
-    out = torch.empty(B, O_out, im_h, im_w, device=dev)
-    step = max(1, 65535 // max(O_out, 1))
-    for s in range(0, B, step):
-        e = min(B, s + step)
-        sl = lambda t: None if t is None else t[s:e]
-        rc = lib.dmm_paste_apply(_p(Bm[s:e]), _p(masks), _p(boxes), _p(src_index[s:e]), e - s, P, O, MS, M, int(padding),
-                                 int(im_h), int(im_w), _p(sl(_counts(n_prop, B, dev))), _p(sl(_counts(n_tmpl, B, dev))),
-                                 _p(sl(row_map)), O_out, int(zero_fill), _p(out[s:e]), O_out * im_h * im_w, _stream())
-        _lib.check(rc, "dmm_paste_apply")
-    return out
+    return _PasteApplyFn.apply(Bm, logic, masks.detach(), boxes.detach(), src_index, _counts(n_prop, B, dev), _counts(n_tmpl, B, dev),
+                               row_map, (int(im_h), int(im_w), O_out, bool(zero_fill), int(padding)))
 
 
 @_op("K9 box_nms")

@@ -257,6 +257,13 @@ int dmm_paste_masks(const float* masks, const float* boxes, int N, int M, int pa
 int dmm_paste_apply(const float* Bmat, const float* masks, const float* boxes, const int* src_index, int B, int P, int O,
                     int MS, int M, int padding, int im_h, int im_w, const int* n_prop, const int* n_tmpl,
                     const int* row_map, int O_out, int zero_fill, float* out, long long out_bstride, void* stream);
+/* Backward of dmm_paste_apply w.r.t. the assignment: g_Bmat[b,o,p] = <g_out[b,row(o)], paste(detection src_index[b,p])> for
+ * the entries with sel[b,o,p] != 0 (the solver's selection mask), 0 elsewhere.  The mask-head outputs carry no gradient
+ * (offline proposals, dmm/modules/model_encoder.py).  Deterministic (fixed-order block reduction). */
+int dmm_paste_apply_bwd(const float* g_out, long long gout_bstride, const float* sel, const float* masks,
+                        const float* boxes, const int* src_index, int B, int P, int O, int MS, int M, int padding,
+                        int im_h, int im_w, const int* n_prop, const int* n_tmpl, const int* row_map, int O_out,
+                        float* g_Bmat, void* stream);
 
 /* ---- K9: box NMS ---------------------------------------------------------------------------------------------
  * Replaces filter_results (dmm/utils/boxlist_ops.py:15-29) -> maskrcnn_benchmark.layers.nms (un-vendored): greedy,

@@ -305,3 +305,64 @@ def test_lazy_pipeline_is_bit_identical_to_paste_nms_match():
         assert torch.equal(out_a, out_b), t
         assert torch.equal(last_a, last_b), t
         assert float(out_a.abs().sum()) > 0
+
+
+def test_lazy_training_equals_paste_all_training():
+    """DMM_Model.forward_lazy (bits-only paste, packed K1 with the targets as second set, K10 with its backward) ==
+    Masker -> filter_results -> DMM_Model.forward in training mode: same outputs and match loss, same gradients into the
+    backbone feature maps (K10's backward against K4's), without materialising the pasted proposal masks."""
+    from dmm_net_b200.utils.boxlist_ops import filter_results
+    from dmm_net_b200.utils.masker import Masker
+    gen = torch.Generator(device=DEV).manual_seed(33)
+    B, F, H, W, C, n_det, P = 3, 4, 64, 96, 16, [23, 17, 30], 12
+    model = DMM_Model(default_cfg(10, 5), is_test=0).to(DEV)
+    valid = torch.tensor([[1, 1, 1, 0], [1, 0, 0, 0], [1, 1, 1, 1]], device=DEV).float()
+
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=gen, device=DEV) * torch.tensor([W * 0.6, H * 0.6], device=DEV)
+        wh = torch.rand(n, 2, generator=gen, device=DEV) * torch.tensor([W * 0.4, H * 0.4], device=DEV) + 4
+        return torch.cat([xy, (xy + wh).clamp(max=min(H, W) - 1)], 1)
+
+    base = [torch.randn(B, C, H // s, W // s, generator=gen, device=DEV) for s in (4, 8, 16, 32)]
+    tb = [boxes(F) for _ in range(B)]
+    masker = Masker(0.5, 1)
+    m0, _ = masker([torch.ones(F, 1, 28, 28, device=DEV)] * B, [BoxList(b, (W, H)) for b in tb])
+    last = torch.stack([m.squeeze(1) for m in m0], 0) * valid[:, :, None, None]
+    targets = (torch.roll(last, 3, dims=3) > 0.5).float()
+    dets = []
+    for b in range(B):
+        d = BoxList(boxes(n_det[b]), (W, H))
+        d.add_field("mask", torch.sigmoid(3 * torch.randn(n_det[b], 1, 28, 28, generator=gen, device=DEV) + 1))
+        d.add_field("scores", torch.rand(n_det[b], generator=gen, device=DEV))
+        dets.append(d)
+    w_out = torch.rand(B, F, H, W, generator=gen, device=DEV)
+
+    def run(lazy):
+        feats = tuple(f.clone().requires_grad_(True) for f in base)
+        tplt = model.fill_template_dict(None, [BoxList(b, (W, H)) for b in tb], {"backbone_feature": feats, "refine_input_feat": feats},
+                                        None, valid)
+        if lazy:
+            out, _, loss, lastn, _ = model.forward_lazy(None, dets, feats, last, tplt, valid, targets, 0.8, P)
+        else:
+            pasted, tight = masker([d.get_field("mask") for d in dets], dets)
+            props = []
+            for b, d in enumerate(dets):
+                bl = BoxList(tight[b].float(), (W, H))
+                bl.add_field("mask", pasted[b])
+                bl.add_field("scores", d.get_field("scores"))
+                props.append(bl)
+            props = filter_results(props, nms_thresh=0.8, max_proposals=P)
+            out, _, loss, lastn = model(None, props, feats, last, tplt, valid, targets)
+        ((out * w_out).sum() + 3.0 * sum(loss)).backward()
+        return out.detach(), torch.stack([x.detach() for x in loss]), lastn.detach(), [f.grad for f in feats]
+
+    out_a, loss_a, last_a, g_a = run(False)
+    out_b, loss_b, last_b, g_b = run(True)
+    np.testing.assert_allclose(out_b.cpu().numpy(), out_a.cpu().numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(last_b.cpu().numpy(), last_a.cpu().numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(loss_b.cpu().numpy(), loss_a.cpu().numpy(), rtol=0, atol=1e-6)
+    assert float(out_a.abs().sum()) > 0 and float(loss_a.abs().sum()) > 0
+    for ga, gb in zip(g_a, g_b):
+        scale = max(1.0, float(ga.abs().max()))
+        np.testing.assert_allclose(gb.cpu().numpy(), ga.cpu().numpy(), rtol=0, atol=2e-5 * scale)
+    assert any(float(g.abs().sum()) > 0 for g in g_a)
