@@ -60,7 +60,9 @@ constexpr int kKC = 32;                         // floats per K chunk (one 128-b
 // traffic (5 stages): stale data converted, arrivals on the wrong phase, pipeline stall.  With an even ring a stage always
 // belongs to the same group and consecutive visits are consecutive phases.
 constexpr int kStages = K5_STAGES;
+#ifndef K5_ALLOW_ODD_RING   // scripts/k5_stress_nccl.py builds the faulty odd ring on purpose to show the race
 static_assert(kStages % 2 == 0, "raw ring depth must be even (see above)");
+#endif
 constexpr int kOpStages = 4;                    // A operand ring in TMEM
 constexpr int kMetaRing = 16;                   // per-chunk metadata (producer leads the MMA warp by < 10 chunks)
 constexpr int kItemRing = 4;
