@@ -521,7 +521,11 @@ def main():
     e2e_threads = args.e2e_threads or max(2, ops.host_threads() // world)
     if world > 1:
         dist.barrier()                                                # all ranks measure at the same time: aggregate rates
-    host_read_gbs, h2d_gbs, read_conc, h2d_conc = host_rooflines(host["prop_mask"], dev, e2e_threads)
+    try:
+        host_read_gbs, h2d_gbs, read_conc, h2d_conc = host_rooflines(host["prop_mask"], dev, e2e_threads)
+    except Exception as exc:                                          # a probe must never cost the headline line
+        print(f"host_rooflines failed: {type(exc).__name__}: {exc}", file=sys.stderr)
+        host_read_gbs = h2d_gbs = read_conc = h2d_conc = 0.0
     if world > 1:
         t = torch.tensor([host_read_gbs, h2d_gbs, read_conc, h2d_conc], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
