@@ -648,6 +648,11 @@ def main():
                     "api": "MatchModel.forward_many_host: pinned host fp32 inputs; the host cores bit-pack most masks (bits "
                            "cross PCIe) while the copy engine DMAs the rest as fp32; features+scores H2D, R and match_score D2H"},
             "gpu_launches": launches,
+            "parity": {"headline_path": "pinned: golden vectors generated from the unmodified reference (tests/golden, oracle/make_golden*.py); "
+                                        "IoU / greedy init / selection bit-exact, floats <= 1e-4, arg-max equal; cpu arm = the reference itself",
+                       "unpinned_by_necessity": ["K5 / K5-TC proposal-feature pooling: ROIAlign lives in the un-vendored maskrcnn_benchmark fork; "
+                                                 "stand-in oracle torchvision roi_align(aligned=False) (secondary legs clip_r50 / eval_r101 / train use it)",
+                                                 "K9 box NMS: same fork; restated from the published algorithm, property-tested"]},
             "secondary": secondary,
             "roofline": {"bound": "hbm", "kernel": "mask_iou_partial_kernel(+finalize)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
