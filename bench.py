@@ -235,7 +235,8 @@ def leg_clip_r50(dev, local_rank):
         r = ce.clip_eval(clips, frames + 1, 50, 10, (H, W), lazy=False, arch="resnet50", fixed_objects=True, time_ops=True)
         rl = ce.clip_eval(clips, frames + 1, 50, 10, (H, W), lazy=True, arch="resnet50", fixed_objects=True)
         clk.mark("end")
-    return {"workload": "configs[2]: ResNet-50 + neck (stock torch) -> K8 paste -> K9 NMS -> K5 pooling -> K2 cosine + K1 IoU -> K3 -> K4 "
+    return {"backbone": "torchvision ResNet-50 + 1x1 necks, eval mode, replayed as one CUDA graph per frame (stock torch.cuda.CUDAGraph)",
+            "workload": "configs[2]: ResNet-50 + neck (stock torch) -> K8 paste -> K9 NMS -> K5 pooling -> K2 cosine + K1 IoU -> K3 -> K4 "
                         "-> K6 pyramid + K7 labels; 8 clips x 8 frames, N=50 K=10 256x448, eval.yaml 40x5, 1 GPU",
             "frames_per_s": r["frames"] / (r["ms"] * 1e-3), "ms_per_frame_step": r["ms_per_frame_step"], "clips_in_flight": clips,
             "lazy_pipeline_frames_per_s": rl["frames"] / (rl["ms"] * 1e-3),
@@ -260,7 +261,8 @@ def leg_eval_r101(dev, local_rank, rank, world):
         clk.mark("end")
     ms = max_over_ranks(r["ms"], dev)
     total_frames = sum_over_ranks(r["frames"], dev)
-    return {"workload": "configs[3]: ResNet-101 + neck (stock torch), synthetic YouTube-VOS-shaped clips: 27 frames, 1..5 of F=5 objects, "
+    return {"backbone": "torchvision ResNet-101 + 1x1 necks, eval mode, replayed as one CUDA graph per frame (stock torch.cuda.CUDAGraph)",
+            "workload": "configs[3]: ResNet-101 + neck (stock torch), synthetic YouTube-VOS-shaped clips: 27 frames, 1..5 of F=5 objects, "
                         "N=50, 255x448, eval.yaml 40x5; DMM_Model.inference_lazy; clips sharded clip % world == rank, no collective",
             "clips": clips_total, "clips_per_gpu": len(mine), "clips_per_s": clips_total / (ms * 1e-3),
             "frames_per_s": total_frames / (ms * 1e-3), "ms_per_frame_step_max_over_ranks": ms / frames,

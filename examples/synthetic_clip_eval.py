@@ -53,9 +53,12 @@ def paste_masks(boxes, H, W, gen):
 
 
 def clip_eval(clips, frames, proposals=50, objects=5, size=(256, 448), lazy=False, arch=None, fixed_objects=False,
-              time_ops=False, seed=4000):
+              time_ops=False, seed=4000, graph_backbone=True):
     """Runs `clips` clips of `frames` frames on THIS rank as one batch per frame; frame 0 is the warm-up.
     arch: None (random feature maps) or a torchvision ResNet name (images -> Encoder -> features, stock torch).
+    graph_backbone: replay the backbone forward as ONE CUDA graph per frame (stock torch.cuda.CUDAGraph): eager, the
+    ~300 small conv / bn / relu launches of a ResNet on 8 images are bound by the host thread issuing them, which is what
+    stops the clip loop from scaling over the GPUs of a box with few host cores.
     Returns dict(frames, ms, ms_per_frame_step, out_shape, op_ms {op: total ms} when time_ops)."""
     dev = torch.device("cuda", torch.cuda.current_device())
     H, W = size
@@ -70,17 +73,34 @@ def clip_eval(clips, frames, proposals=50, objects=5, size=(256, 448), lazy=Fals
     n_obj = torch.full((B,), F, device=dev) if fixed_objects else torch.randint(1, F + 1, (B,), generator=gen, device=dev)
     valid = (torch.arange(F, device=dev)[None, :] < n_obj[:, None]).float()
 
+    graph = None
+    if enc is not None and graph_backbone:
+        img_static = torch.randn(B, 3, H, W, generator=gen, device=dev)
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm), torch.no_grad():             # cuDNN picks its algorithms outside the capture
+            for _ in range(3):
+                enc(img_static)
+        torch.cuda.current_stream().wait_stream(warm)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            feats_static = enc(img_static)
+
     def feats():
         if enc is None:
             return tuple(torch.randn(B, C, -(-H // s), -(-W // s), generator=gen, device=dev) for s in (4, 8, 16, 32))
-        return enc(torch.randn(B, 3, H, W, generator=gen, device=dev))
+        if graph is None:
+            return enc(torch.randn(B, 3, H, W, generator=gen, device=dev))
+        img_static.normal_(generator=gen)                           # the frame's images land in the graph's input buffer
+        graph.replay()
+        return feats_static                                         # overwritten by the next replay: consumed within the frame
 
     timer = ops.KernelTimer() if time_ops else None
     backbone_ev = []
     # frame 0: ground-truth boxes/masks define the templates
     tboxes = [random_boxes(gen, F, H, W, dev) for _ in range(B)]
     with torch.no_grad():
-        f0 = feats()
+        f0 = tuple(f.clone() for f in feats())                       # templates keep views of frame 0's features
         tplt = model.fill_template_dict(None, [BoxList(b) for b in tboxes], {"backbone_feature": f0, "refine_input_feat": f0},
                                         None, valid)
     mask_last = torch.stack([paste_masks(b, H, W, gen).squeeze(1) for b in tboxes], 0) * valid[:, :, None, None]
