@@ -348,15 +348,23 @@ def run_leg(name, world, index):
     env = {k: v for k, v in os.environ.items()
            if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "ROLE_WORLD_SIZE",
                         "GROUP_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT") and not k.startswith("TORCHELASTIC_")}
+    import signal
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
+        out, err = proc.communicate(timeout=600)
     except subprocess.TimeoutExpired:
-        return {"error": "leg timed out after 600 s"}
-    for line in reversed(r.stdout.splitlines()):
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)                      # the leg's own session: torchrun and every rank under it
+        except OSError:
+            pass
+        proc.communicate()
+        return {"error": "leg timed out after 600 s (its process group was killed)"}
+    for line in reversed(out.splitlines()):
         if line.startswith('{"leg"'):
             return json.loads(line)["result"]
-    tail = [x for x in r.stderr.splitlines() if x.strip() and "Warning" not in x][-6:]
-    return {"error": f"leg exited with code {r.returncode}", "stderr_tail": tail}
+    tail = [x for x in err.splitlines() if x.strip() and "Warning" not in x][-6:] + \
+           [x for x in out.splitlines() if x.startswith("libdmm_b200")][:3]
+    return {"error": f"leg exited with code {proc.returncode}", "stderr_tail": tail}
 
 
 def host_rooflines(host_masks, dev, threads):

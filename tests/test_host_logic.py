@@ -93,3 +93,29 @@ def test_cosine_impl_names_and_packed_word_count():
     h, w = ctypes.c_int(), ctypes.c_int()
     assert lib.dmm_mask_pyramid_level_size(255, 447, 3, ctypes.byref(h), ctypes.byref(w)) == 0 and (h.value, w.value) == (8, 14)
     assert lib.dmm_mask_pyramid_level_size(255, 447, 5, ctypes.byref(h), ctypes.byref(w)) == 1      # more than 5 levels
+
+
+def test_hostmem_helpers_degrade_gracefully():
+    """dmm_net_b200/hostmem.py: NUMA placement of pinned buffers is best effort -- on a single-node host (the GPU boxes are
+    single-node VMs) everything must still work and say so."""
+    from dmm_net_b200 import hostmem
+    nodes = hostmem.memory_nodes()
+    assert isinstance(nodes, list) and len(nodes) >= 1 and all(isinstance(n, int) for n in nodes)
+    with hostmem.prefer_node(None) as ok:
+        assert ok is False
+    with hostmem.prefer_node(10 ** 6) as ok:                       # a node that does not exist: refused, not raised
+        assert ok is False
+    with hostmem.prefer_node(nodes[0]) as ok:
+        t = torch.zeros(1024)
+        assert isinstance(ok, bool) and float(t.sum()) == 0.0
+
+
+def test_solver_shape_limits_are_reported_with_the_reference_flag_names():
+    from dmm_net_b200 import ops
+    lim = ops.limits()
+    assert lim["max_templates"] == 16 and lim["max_solver_cols"] == 128
+    ops.check_solver_shape(50, 10)
+    with pytest.raises(RuntimeError, match="maxseqlen"):
+        ops.check_solver_shape(50, 17)
+    with pytest.raises(RuntimeError, match="sort_max_num"):
+        ops.check_solver_shape(129, 5)
