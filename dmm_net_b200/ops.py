@@ -1078,6 +1078,7 @@ def _pinned(key, shape, dtype):
 _HOST_SPLIT = {}          # (P, O, HW) -> best measured seconds per problem of the two routes (pack, dma)
 _HOST_PENDING = {}        # (P, O, HW) -> measurements of the previous call, not yet folded in
 _STAGE_TURN, _STAGE_EVENT = {}, {}   # double-buffered pinned staging: next slot, and the H2D-done event of each slot
+_RAW_TURN, _RAW_STAGE = {}, {}       # raw route: next device slot; (key, slot) -> [prop buffer, tmpl buffer, last-read event]
 
 
 def _fold_route_measurement(key):
@@ -1172,11 +1173,25 @@ def _match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *,
     t_call = time.perf_counter()
     pm_raw = tm_raw = None
     ev_dma = None
+    raw_slot = None
     if nraw > 0:
-        copy_stream = _side_streams(dev)[0]                    # not ordered after `main`: the DMA may start while the previous
-        with torch.cuda.stream(copy_stream):                   # call's kernels still run (fresh buffers, read-only source)
-            pm_raw = torch.empty((nraw, P, HW), device=dev)    # allocate first: a cudaMalloc inside the timed pair would
-            tm_raw = torch.empty((nraw, O, HW), device=dev)    # be booked as DMA time
+        # Device staging of the raw route: two persistent slots of full-batch size, alternated call by call.  (Fresh
+        # tensors per call on the side stream went through the caching allocator with a size that follows the moving
+        # split: every new size is a cudaMalloc -- milliseconds, and a device-wide synchronisation -- inside the call.)
+        # Slot k is overwritten only after the K1 launch that read it two calls ago has finished (event on `main`).
+        raw_slot = _RAW_TURN.get(key, 0)
+        _RAW_TURN[key] = raw_slot ^ 1
+        st = _RAW_STAGE.get((key, raw_slot))
+        copy_stream = _side_streams(dev)[0]
+        if st is None or st[0].shape[0] < B:
+            copy_stream.synchronize()                          # a larger batch than before: no DMA may still target the old slot
+            st = [torch.empty((B, P, HW), device=dev), torch.empty((B, O, HW), device=dev), None]
+            _RAW_STAGE[(key, raw_slot)] = st
+        # copy_stream is not ordered after `main`: the DMA may start while the previous
+        with torch.cuda.stream(copy_stream):                   # call's kernels still run (the other slot, read-only source)
+            if st[2] is not None:
+                copy_stream.wait_event(st[2])
+            pm_raw, tm_raw = st[0][:nraw], st[1][:nraw]
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
             pm_raw.copy_(prop_mask[:nraw], non_blocking=True)
@@ -1221,12 +1236,13 @@ def _match_batch_host(prop_feat, prop_mask, tmpl_feat, tmpl_mask, prop_score, *,
                                                 w_cos=1 - w, w_iou=w)
         if nraw > 0:
             main.wait_event(ev_dma)
-            pm_raw.record_stream(main)
-            tm_raw.record_stream(main)
             consumed = torch.cuda.Event()
             consumed.record(main)                                # after the wait on the raw DMA and every copy queued on main
             parts[0] = mask_iou_pairwise(pm_raw, tm_raw, None, sl(n_prop, 0, nraw), sl(n_tmpl, 0, nraw), cos=cos[:nraw],
                                          w_cos=1 - w, w_iou=w)
+            read_done = torch.cuda.Event()
+            read_done.record(main)                               # the slot may be overwritten once this K1 has run
+            _RAW_STAGE[(key, raw_slot)][2] = read_done
         parts = [q for q in parts if q is not None]
         if len(parts) == 1:
             iou, sim = parts[0]["iou"], parts[0]["sim"]
