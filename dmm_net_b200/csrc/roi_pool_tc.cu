@@ -779,7 +779,9 @@ bool make_plan(const int Hl[4], const int Wl[4], int N, int C, int R, Plan& pl) 
   for (int l = 0; l < 4; ++l) { kp.lv[l].wx_off = wx_off; wx_off += kNR * kp.lv[l].Wp; }
   kp.wtab_stride = (wx_off + 3) / 4 * 4;
   // ~4 work items per SM at one group per frame; items between 8 and 64 chunks
-  long long target = chunks_per_group * N / (kNumSMs * 4);
+  int per_sm = 4;
+  if (const char* e = getenv("DMM_K5_ITEMS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) per_sm = v; }   // tuning knob
+  long long target = chunks_per_group * N / (kNumSMs * (long long)per_sm);
   target = std::min<long long>(64, std::max<long long>(8, target));
   int item0 = 0;
   for (int l = 0; l < 4; ++l) {
