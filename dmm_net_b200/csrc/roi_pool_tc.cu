@@ -52,7 +52,8 @@ constexpr int kKC = 32;                         // floats per K chunk (one 128-b
 #ifndef K5_STAGES
 #define K5_STAGES 4
 #endif
-// Raw fp32 ring (what the TMA keeps in flight: 4 x 16 KB; measured: 2, 3 and 5 stages run at the same speed).  MUST BE EVEN:
+// Raw fp32 ring (what the TMA keeps in flight: 4 x 16 KB; measured at 64 frames x 50 ROIs: 2 stages 150 us, 4 stages 136 us --
+// the ring is not the limiter, the converter -> MMA -> epilogue hand-offs are).  MUST BE EVEN:
 // the two converter groups take alternate chunks, and a waiter tests the PARITY of an mbarrier phase.  With an odd ring
 // the groups alternate on every stage, so a group's consecutive visits to a stage are two phases apart -- same parity --
 // and its wait for chunk g+2*kStages passes as soon as phase g has completed, i.e. possibly BEFORE chunk g+kStages (the
