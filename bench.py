@@ -616,17 +616,22 @@ def main():
     leg_out = {}
     import datetime
     del host
-    ctl = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=45)) if world > 1 and legs else None
+    ctl = None
+    if world > 1 and legs:
+        try:                                                          # host-side waiting: the idle ranks must not spin on the GPU
+            ctl = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=45))
+        except Exception as exc:
+            print(f"gloo control group unavailable ({type(exc).__name__}: {exc}); the ranks wait on an NCCL barrier instead", file=sys.stderr)
     if legs:
         torch.cuda.synchronize()
-        if ctl is not None:
-            dist.barrier(group=ctl)
+        if world > 1:
+            dist.barrier(group=ctl) if ctl is not None else dist.barrier()
         if rank == 0:
             names = {"clip": "clip_r50", "eval": "eval_r101", "train": "train"}
             for i, name in enumerate(legs):
                 leg_out[names.get(name, name)] = run_leg(name, world, i)
-        if ctl is not None:
-            dist.barrier(group=ctl)
+        if world > 1:
+            dist.barrier(group=ctl) if ctl is not None else dist.barrier()
     if secondary is None:
         secondary = {}
     secondary.update(leg_out)
